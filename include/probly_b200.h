@@ -1,0 +1,232 @@
+/*
+ * probly_b200.h — C ABI of the B200-native query hot path of probly-search.
+ *
+ * This is the drop-in seam UNDER the reference's `Index::query` (src/query.rs:21-106): the
+ * reference has no FFI of its own (crate-type cdylib but no #[no_mangle] item anywhere,
+ * Cargo.toml:25-26), so these entry points are what a Rust shim (rust/src/lib.rs in this repo,
+ * unbuilt — no rustc in the image) binds with `extern "C"`.  Plain pointers and sizes only; no
+ * torch / C++ types cross the boundary.  See INTEGRATION.md for the binding stubs.
+ *
+ * Ownership: the caller owns every buffer it passes in or receives results in; the library
+ * copies what it needs and owns only its opaque handles (+ their host/device memory).
+ * Errors: 0 = ok, negative = error code; nothing throws or aborts across the ABI; a
+ * thread-local message is available from pb_last_error().  (The reference panics instead:
+ * `unwrap()` at src/query.rs:46,63,70 and the NaN sort at :103.)
+ * Threading: a pb_builder needs external exclusion for mutation (mirrors `&mut self`); a
+ * pb_index is immutable between pb_index_create / pb_index_set_live_state calls; each
+ * pb_batch owns its workspace and stream, so batches on one index may run concurrently
+ * from different host threads (mirrors `query(&self, ..)`, src/query.rs:22).
+ *
+ * There is NO CPU fallback: every query entry point fails with PB_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ */
+#ifndef PROBLY_B200_H
+#define PROBLY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK 0
+#define PB_ERR_INVALID (-1)      /* bad argument / malformed input */
+#define PB_ERR_CUDA (-2)         /* a CUDA runtime call failed */
+#define PB_ERR_NO_DEVICE (-3)    /* no usable CUDA device (there is no CPU fallback) */
+#define PB_ERR_CAPACITY (-4)     /* caller-provided output buffer too small */
+#define PB_ERR_UNSUPPORTED (-5)  /* outside the supported envelope (see limits below) */
+#define PB_ERR_DUPLICATE_KEY (-6)
+#define PB_ERR_NOMEM (-7)
+
+/* ScoreCalculator implementations that exist on the device (src/score/default/{bm25,zero_to_one}.rs).
+ * Any other `impl ScoreCalculator` is arbitrary host code and cannot run here. */
+#define PB_SCORER_BM25 0u
+#define PB_SCORER_ZERO_TO_ONE 1u
+
+#define PB_MAX_FIELDS 4u   /* Index::new(fields_num) with fields_num <= 4 */
+#define PB_MAX_TOP_K 32u   /* per-query top-k kept by the batch entry point */
+#define PB_MAX_QUERY_TERMS 4095u
+
+typedef struct pb_builder pb_builder; /* host-side mutable index: the L1 of src/index.rs:19-33 */
+typedef struct pb_index pb_index;     /* immutable flattened image resident in HBM on one device */
+typedef struct pb_batch pb_batch;     /* one uploaded query batch + its device workspace */
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side index maintenance (replaces Index::new / add_document / remove_document / vacuum,
+ * src/index.rs:37-60, 77-158, 161-191, 194-241 — as semantics; the data layout is new).
+ * Tokens arrive PRE-TOKENIZED: field accessors (src/lib.rs:11) and the tokenizer
+ * (src/lib.rs:14) are user function pointers and stay in the binding layer.
+ * ---------------------------------------------------------------------------------------- */
+
+/* One document's tokens.  Tokens of all values of all fields are concatenated in
+ * (field, value, token) order; empty tokens are passed through (they are skipped exactly
+ * where src/index.rs:101 skips them). */
+typedef struct pb_doc_tokens {
+  const uint8_t* tok_bytes;          /* UTF-8 bytes of all tokens, concatenated */
+  const uint64_t* tok_off;           /* [n_tokens + 1] byte offsets into tok_bytes */
+  const uint32_t* value_tok_count;   /* one entry per field VALUE: its token count */
+  const uint32_t* field_value_count; /* [num_fields]: how many values the accessor returned */
+} pb_doc_tokens;
+
+int pb_builder_create(uint32_t num_fields, pb_builder** out);          /* Index::new, index.rs:37 */
+void pb_builder_destroy(pb_builder* b);
+int pb_builder_add_document(pb_builder* b, uint64_t key, const pb_doc_tokens* doc); /* index.rs:77 */
+/* Bulk add: n_docs documents, every field has exactly one value; field_tok_count is
+ * [n_docs * num_fields]; tokens concatenated in (doc, field, token) order. */
+int pb_builder_add_documents(pb_builder* b, uint64_t n_docs, const uint64_t* keys,
+                             const uint8_t* tok_bytes, const uint64_t* tok_off,
+                             const uint32_t* field_tok_count);
+int pb_builder_remove_document(pb_builder* b, uint64_t key);           /* index.rs:161 (lazy) */
+int pb_builder_vacuum(pb_builder* b);                                  /* index.rs:194 */
+
+typedef struct pb_builder_info {
+  uint32_t num_fields;
+  uint64_t n_live_docs;       /* docs.len() */
+  uint64_t n_doc_ordinals;    /* ordinals ever assigned and still referenced */
+  uint64_t n_removed_pending; /* removed but not yet vacuumed */
+  uint64_t n_terms;           /* trie nodes that own at least one posting */
+  uint64_t n_nodes;           /* live trie nodes, root included (count_nodes, index.rs:464-480) */
+  uint64_t n_rows;            /* de-duplicated (term, doc) posting rows */
+  uint64_t n_pointers;        /* reference DocumentPointer count = sum of multiplicities */
+  uint64_t field_sum[PB_MAX_FIELDS]; /* FieldDetails.sum, index.rs:391-396 */
+  double field_avg[PB_MAX_FIELDS];   /* FieldDetails.avg */
+} pb_builder_info;
+int pb_builder_get_info(const pb_builder* b, pb_builder_info* out);
+
+/* The flattened, immutable image: what lives in HBM.  All pointers are HOST pointers owned
+ * by the builder and stay valid until the builder is mutated or destroyed.
+ *   - trie: nodes renumbered in DFS pre-order with children in the reference's linked-list
+ *     order (most recently created child first, index.rs:409-419), so the expansions of a
+ *     prefix (query.rs:109-147) are the contiguous, already ordered term range
+ *     [node_term_lo, node_term_hi).  Edges of a node are stored sorted by char (lookup only).
+ *   - postings: one row per (term, doc), rows of a term contiguous, terms in DFS order, docs
+ *     ascending by ordinal inside a term; structure-of-arrays columns doc / tf[f] / fl[f],
+ *     every column padded to a multiple of 128 rows (pad rows are zero).
+ *   - live state: removed-but-not-vacuumed bitmap, live doc count, per-field average. */
+typedef struct pb_index_image {
+  uint32_t version;     /* = 1 */
+  uint32_t num_fields;
+  uint64_t n_nodes, n_edges, n_terms, n_rows, n_rows_padded, n_docs;
+  uint32_t max_term_bytes;
+  uint32_t max_tf[PB_MAX_FIELDS];
+  uint32_t max_fl[PB_MAX_FIELDS];
+  const uint32_t* node_edge_begin; /* [n_nodes + 1] */
+  const uint32_t* node_term_lo;    /* [n_nodes] */
+  const uint32_t* node_term_hi;    /* [n_nodes] */
+  const uint32_t* node_parent;     /* [n_nodes] (host-only: to rebuild term strings) */
+  const uint32_t* node_char;       /* [n_nodes] Unicode scalar on the edge into the node */
+  const uint32_t* edge_char;       /* [n_edges] sorted ascending inside each node */
+  const uint32_t* edge_child;      /* [n_edges] */
+  const uint64_t* term_row_begin;  /* [n_terms + 1] */
+  const uint32_t* term_byte_len;   /* [n_terms] UTF-8 byte length (bm25.rs:51-52, zero_to_one.rs:57-58) */
+  const uint32_t* term_node;       /* [n_terms] */
+  const uint32_t* post_doc;        /* [n_rows_padded] */
+  const uint32_t* post_tf[PB_MAX_FIELDS];
+  const uint32_t* post_fl[PB_MAX_FIELDS];
+  const uint64_t* doc_key;         /* [n_docs] ordinal -> caller's key */
+  const uint32_t* removed_bitmap;  /* [(n_docs + 31) / 32] bit set = not live */
+  uint64_t n_removed;
+  uint64_t n_live_docs;
+  double field_avg[PB_MAX_FIELDS];
+} pb_index_image;
+int pb_builder_flatten(pb_builder* b, pb_index_image* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Device image
+ * ---------------------------------------------------------------------------------------- */
+int pb_device_count(void);
+int pb_index_create(const pb_index_image* image, int device, pb_index** out);
+/* New removed set / N / avg after remove_document WITHOUT re-flattening (pre-vacuum state,
+ * SURVEY §3.4 rule 9).  removed_ords is the FULL set of removed ordinals.  Recomputes the
+ * per-term live occurrence count (count_documents, index.rs:282-297) on the device and the
+ * idf table (bm25.rs:41-56) on the host with libm log. */
+int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t n_removed,
+                            uint64_t n_live_docs, const double* field_avg);
+void pb_index_destroy(pb_index* ix);
+/* expand_term (query.rs:109-126) through the device descent kernel: the expansions of `term`
+ * joined by '\n' into out (cap bytes).  *n_expansions / *needed are always set. */
+int pb_index_expand_term(pb_index* ix, const uint8_t* term, uint64_t term_len, uint8_t* out,
+                         uint64_t cap, uint64_t* n_expansions, uint64_t* needed);
+/* Per-term live occurrence count as the device computed it (tests). */
+int pb_index_term_df_live(pb_index* ix, uint64_t* out, uint64_t cap);
+
+/* ------------------------------------------------------------------------------------------
+ * Queries (replaces Index::query, src/query.rs:21-106, for batches)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pb_query_batch_desc {
+  uint64_t n_queries;
+  const uint64_t* query_term_off; /* [n_queries + 1] indices into the term arrays; the terms of a
+                                     query are ALL tokens the tokenizer produced, empty ones
+                                     included (query.rs:32-35) */
+  const uint64_t* term_byte_off;  /* [n_terms + 1] byte offsets into term_bytes */
+  const uint8_t* term_bytes;      /* UTF-8 */
+  uint32_t scorer;                /* PB_SCORER_* */
+  double bm25_k1, bm25_b;         /* BM25 { bm25k1, bm25b }, bm25.rs:14-26 */
+  const double* fields_boost;     /* [num_fields] (query.rs:26); finite values */
+  uint32_t n_fields_boost;
+  uint32_t top_k;                 /* <= PB_MAX_TOP_K */
+} pb_query_batch_desc;
+
+/* Per-query outputs.  Any pointer may be NULL (that output is skipped).
+ * Digests (order independent, wrap-around sums over the result set):
+ *   h(d)        = x=(d+1)*0x9E3779B97F4A7C15; x^=x>>32; x*=0xD6E8FEB86659FD93; x^=x>>32
+ *   doc_digest  = sum h(doc ordinal)
+ *   score_digest= sum g(d,s), g = y=(h(d)^bits(s))*0xD6E8FEB86659FD93; y^=y>>32
+ * top-k rows are ordered (score desc, doc ordinal asc) — the reference's comparison rule
+ * (src/lib.rs:54-58) when ordinals follow key order. */
+typedef struct pb_query_results {
+  uint64_t* n_results;    /* [n_queries] size of the full result set (query.rs:97-100) */
+  uint64_t* doc_digest;   /* [n_queries] */
+  uint64_t* score_digest; /* [n_queries] */
+  uint32_t* topk_n;       /* [n_queries] = min(top_k, n_results) */
+  uint32_t* topk_doc;     /* [n_queries * top_k] doc ordinals */
+  double* topk_score;     /* [n_queries * top_k] */
+} pb_query_results;
+
+/* One call, host buffers in / host buffers out (upload + kernels + download). */
+int pb_query_batch(pb_index* ix, const pb_query_batch_desc* q, pb_query_results* out);
+
+/* The same three stages separately: upload once, run (device-resident inputs), fetch. */
+int pb_batch_create(pb_index* ix, const pb_query_batch_desc* q, pb_batch** out);
+int pb_batch_run(pb_batch* b);
+int pb_batch_fetch(pb_batch* b, pb_query_results* out);
+void pb_batch_destroy(pb_batch* b);
+
+typedef struct pb_batch_stats {
+  uint64_t n_queries, n_query_terms;
+  uint64_t n_segments;        /* (query term, expanded term) posting lists walked */
+  uint64_t rows_streamed;     /* posting rows read by the scoring kernel (direct + diverted) */
+  uint64_t rows_streamed_direct; /* ... of which by the single launch over all single-list queries */
+  uint64_t rows_scored;       /* rows whose doc is live = ScoreCalculator::score evaluations on
+                                 de-duplicated rows ("scored postings") */
+  uint64_t rows_diverted;     /* rows routed through the sort+fold side path */
+  uint64_t results_emitted;   /* sum of n_results */
+  uint64_t pointer_visits;    /* reference-equivalent DocumentPointer visits (sum of multiplicities) */
+  uint32_t gpu_launches;      /* kernels launched by the last pb_batch_run */
+  uint32_t side_rounds;       /* sub-batches of the side path */
+  float ms_total;             /* CUDA-event time of the last pb_batch_run on its stream */
+  float ms_descend, ms_plan, ms_score, ms_side, ms_finalize;
+  uint32_t score_launches;    /* launches of the scoring kernel inside ms_score */
+} pb_batch_stats;
+int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out);
+/* Stats of the last pb_query_batch / pb_query_full call on this index. */
+int pb_index_last_stats(pb_index* ix, pb_batch_stats* out);
+
+/* Full result sets (parity sampling; what Index::query returns): every (query, doc, score) of
+ * every query of the batch, in no particular order.  *n_total is always set; returns
+ * PB_ERR_CAPACITY when cap is too small (nothing useful written). */
+int pb_query_full(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint32_t* out_query,
+                  uint32_t* out_doc, double* out_score, uint64_t* n_total);
+
+/* Pinned host memory for the buffers of pb_query_batch (optional; any host memory works). */
+void* pb_host_alloc(size_t bytes);
+void pb_host_free(void* p);
+
+const char* pb_last_error(void);
+const char* pb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROBLY_B200_H */

@@ -1,0 +1,890 @@
+// Host orchestration of the device query path + the pb_index / pb_batch half of the C ABI
+// (include/probly_b200.h).  One pb_index = one flattened image resident in HBM on one device;
+// one pb_batch = one uploaded query batch, its stream and its workspace.
+//
+// pb_batch_run pipeline (all on the batch's stream):
+//   descend -> plan (classify, segment descriptors, tile prefix sums) -> score kernel over all
+//   single-list queries (the dominant launch) -> rounds of the multi-list side path
+//   (mark / score+divert / radix sort / fold / clear) -> finalize (merge partial top-k lists).
+// There is no CPU fallback anywhere in this file: without a device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "common.hpp"
+#include "kernels.cuh"
+
+using namespace pbk;
+typedef unsigned long long ull;
+
+#define CU(x)                                                                                    \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess) {                                                                     \
+      pb::set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+      return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? PB_ERR_NO_DEVICE   \
+                                                                            : PB_ERR_CUDA;       \
+    }                                                                                            \
+  } while (0)
+#define RC(x)                  \
+  do {                         \
+    int rc_ = (x);             \
+    if (rc_ != PB_OK) return rc_; \
+  } while (0)
+
+namespace {
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t c = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void**)&p, c * sizeof(T));
+    if (e == cudaSuccess) cap = c;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  ~DBuf() { release(); }
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+};
+
+template <class T>
+cudaError_t upload(DBuf<T>& d, const T* h, size_t n, size_t extra_zero = 0) {
+  cudaError_t e = d.ensure(n + extra_zero + 1);
+  if (e != cudaSuccess) return e;
+  if (n) { e = cudaMemcpy(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice); if (e != cudaSuccess) return e; }
+  return cudaMemset(d.p + n, 0, (extra_zero + 1) * sizeof(T));
+}
+
+uint32_t bits_for(uint64_t n) {   // bits needed to represent values 0..n-1 (at least 1)
+  uint32_t b = 1;
+  while ((1ull << b) < n) ++b;
+  return b;
+}
+
+int g_sm_count(int device) {
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  return n;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// pb_index
+// ==========================================================================================
+struct pb_index {
+  int device = 0;
+  int sm_count = 148;
+  uint32_t F = 1;
+  uint64_t n_nodes = 0, n_edges = 0, n_terms = 0, n_rows = 0, n_rows_padded = 0, n_docs = 0;
+  uint32_t max_term_bytes = 0, max_tf[4] = {0, 0, 0, 0}, max_fl[4] = {0, 0, 0, 0};
+  DBuf<uint32_t> node_edge_begin, node_term_lo, node_term_hi, edge_char, edge_child;
+  DBuf<uint64_t> term_row_begin;
+  DBuf<uint32_t> term_byte_len, post_doc, post_tf[4], post_fl[4], removed, live_prefix;
+  DBuf<uint64_t> term_df_live, liverows_prefix;
+  DBuf<double> term_idf, eb;
+  // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
+  std::vector<uint32_t> h_node_parent, h_node_char, h_term_node;
+  std::vector<uint64_t> h_term_row_begin, h_df_live;
+  uint64_t n_live = 0, n_removed = 0;
+  double avg[4] = {0, 0, 0, 0};
+  std::mutex mu;                 // guards `scratch`
+  pb_batch* scratch = nullptr;   // reused by pb_query_batch / pb_query_full / expand_term
+
+  IndexView view() const {
+    IndexView v;
+    v.node_edge_begin = node_edge_begin.p; v.node_term_lo = node_term_lo.p; v.node_term_hi = node_term_hi.p;
+    v.edge_char = edge_char.p; v.edge_child = edge_child.p;
+    v.term_row_begin = term_row_begin.p; v.term_byte_len = term_byte_len.p;
+    v.post_doc = post_doc.p;
+    for (int f = 0; f < 4; ++f) { v.post_tf[f] = post_tf[f].p; v.post_fl[f] = post_fl[f].p; }
+    v.removed = removed.p;
+    v.term_df_live = term_df_live.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
+    v.term_idf = term_idf.p; v.eb = eb.p;
+    v.n_terms = (uint32_t)n_terms; v.n_docs = (uint32_t)n_docs; v.num_fields = F;
+    v.has_removed = n_removed ? 1u : 0u;
+    return v;
+  }
+};
+
+static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, uint64_t n_removed,
+                                  uint64_t n_live, const double* avg) {
+  CU(cudaSetDevice(ix->device));
+  const size_t words = (ix->n_docs + 31) / 32 + 1;
+  CU(ix->removed.ensure(words));
+  CU(cudaMemcpy(ix->removed.p, bitmap_words, words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  ix->n_removed = n_removed;
+  ix->n_live = n_live;
+  for (uint32_t f = 0; f < ix->F; ++f) ix->avg[f] = avg[f];
+  const size_t NT = ix->n_terms;
+  CU(ix->term_df_live.ensure(NT + 1));
+  CU(ix->live_prefix.ensure(NT + 2));
+  CU(ix->liverows_prefix.ensure(NT + 2));
+  CU(ix->term_idf.ensure(NT + 1));
+  CU(cudaMemset(ix->term_df_live.p, 0, (NT + 1) * sizeof(uint64_t)));
+  if (NT) {
+    IndexView v = ix->view();
+    int grid = ix->sm_count * 8;
+    switch (ix->F) {
+      case 1: live_df_kernel<1><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
+      case 2: live_df_kernel<2><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
+      case 3: live_df_kernel<3><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
+      default: live_df_kernel<4><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
+    }
+    CU(cudaGetLastError());
+  }
+  ix->h_df_live.assign(NT + 1, 0);
+  CU(cudaMemcpy(ix->h_df_live.data(), ix->term_df_live.p, NT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  // BM25::before_each, bm25.rs:41-56: idf from the LIVE doc count and the clamped live df.
+  // libm `log` on the host = what Rust's f64::ln calls, so the table is bit-identical.
+  std::vector<double> idf(NT + 1, 0.0);
+  std::vector<uint32_t> lp(NT + 2, 0);
+  std::vector<uint64_t> lrp(NT + 2, 0);
+  for (size_t t = 0; t < NT; ++t) {
+    uint64_t df = ix->h_df_live[t];
+    uint64_t frequency = std::min<uint64_t>(n_live, df);
+    uint64_t diff = n_live - frequency;
+    idf[t] = std::log(1.0 + ((double)diff + 0.5) / ((double)frequency + 0.5));
+    lp[t + 1] = lp[t] + (df > 0 ? 1u : 0u);
+    lrp[t + 1] = lrp[t] + (df > 0 ? (ix->h_term_row_begin[t + 1] - ix->h_term_row_begin[t]) : 0);
+  }
+  CU(cudaMemcpy(ix->term_idf.p, idf.data(), (NT + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ix->live_prefix.p, lp.data(), (NT + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ix->liverows_prefix.p, lrp.data(), (NT + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  return PB_OK;
+}
+
+// ==========================================================================================
+// pb_batch
+// ==========================================================================================
+struct pb_batch {
+  pb_index* ix = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  uint64_t Q = 0, NT = 0;
+  uint32_t scorer = 0, k = 0;
+  double k1 = 1.2, b = 0.75, boost[4] = {1, 1, 1, 1};
+  bool loaded = false, ran = false;
+  // capture of full result sets
+  uint64_t full_cap = 0;
+  DBuf<uint32_t> full_q, full_doc;
+  DBuf<double> full_score;
+  DBuf<ull> full_count;
+  // inputs
+  DBuf<uint8_t> term_bytes;
+  DBuf<uint64_t> term_byte_off, query_term_off;
+  // plan
+  DBuf<uint32_t> qt_lo, qt_hi, qt_len, qt_q;
+  DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_gsegoff, q_gtileoff;
+  DBuf<ull> s_tiles, s_tile_off, g_tiles, g_tile_off;
+  DBuf<Seg> seg_s, seg_g;
+  DBuf<uint8_t> cub_temp;
+  // outputs
+  DBuf<ull> n_results, doc_digest, score_digest;
+  DBuf<uint32_t> topk_n, topk_doc;
+  DBuf<double> topk_score;
+  // partial lists + counters
+  DBuf<uint32_t> part_head, part_next, part_n, part_doc, counters;   // counters: [0] part_count [1] rec_count [2] error
+  DBuf<double> part_score;
+  DBuf<ull> stats;            // [2][ST_COUNT]: S phase, G phase
+  // side path
+  DBuf<uint32_t> bitmap;
+  size_t bitmap_zeroed = 0;
+  DBuf<ull> rec_key, rec_val, rec_key2, rec_val2;
+  // BM25 table
+  DBuf<double> tab;
+  uint32_t tab_tfcap[4] = {}, tab_flcap[4] = {}, tab_off[4] = {}, tab_total = 0;
+  // host staging
+  std::vector<ull> h_recoff, h_gidx, h_gsegoff, h_gtileoff;
+  pb_batch_stats st{};
+
+  ~pb_batch() {
+    if (ix) cudaSetDevice(ix->device);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int scan_ull(pb_batch* b, const ull* in, ull* out, size_t n_plus_1) {
+  size_t bytes = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n_plus_1, b->stream));
+  CU(b->cub_temp.ensure(bytes));
+  bytes = b->cub_temp.cap;
+  CU(cub::DeviceScan::ExclusiveSum(b->cub_temp.p, bytes, in, out, (int64_t)n_plus_1, b->stream));
+  return PB_OK;
+}
+
+__global__ void gather_tileoff_kernel(uint64_t n, const ull* __restrict__ q_gsegoff,
+                                      const ull* __restrict__ g_tile_off, ull* __restrict__ q_gtileoff) {
+  uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (q < n) q_gtileoff[q] = g_tile_off[q_gsegoff[q]];
+}
+
+double bm25_tf_host(double k1, double b, double avg, uint32_t tf, uint32_t fl) {
+  // bm25.rs:78-82 — same operation order; this file is compiled with -ffp-contract=off
+  double tfd = (double)tf;
+  return ((k1 + 1.0) * tfd) / (k1 * ((1.0 - b) + b * ((double)fl / avg)) + tfd);
+}
+
+int batch_build_table(pb_batch* b) {
+  pb_index* ix = b->ix;
+  uint32_t tfc[4], flc[4];
+  for (uint32_t f = 0; f < ix->F; ++f) {
+    tfc[f] = std::min<uint32_t>(ix->max_tf[f] + 1, 64);
+    flc[f] = std::min<uint32_t>(ix->max_fl[f] + 1, 1024);
+  }
+  auto total = [&]() { uint64_t t = 0; for (uint32_t f = 0; f < ix->F; ++f) t += (uint64_t)tfc[f] * flc[f]; return t; };
+  while (total() > 4096) {     // 32 KB of shared memory
+    uint32_t best = 0;
+    for (uint32_t f = 1; f < ix->F; ++f) if ((uint64_t)tfc[f] * flc[f] > (uint64_t)tfc[best] * flc[best]) best = f;
+    if (tfc[best] > 4) tfc[best] = (tfc[best] + 1) / 2;
+    else if (flc[best] > 2) flc[best] = (flc[best] + 1) / 2;
+    else break;
+  }
+  std::vector<double> h;
+  uint32_t off = 0;
+  for (uint32_t f = 0; f < 4; ++f) { b->tab_tfcap[f] = 0; b->tab_flcap[f] = 0; b->tab_off[f] = 0; }
+  for (uint32_t f = 0; f < ix->F; ++f) {
+    b->tab_tfcap[f] = tfc[f]; b->tab_flcap[f] = flc[f]; b->tab_off[f] = off;
+    for (uint32_t tf = 0; tf < tfc[f]; ++tf)
+      for (uint32_t fl = 0; fl < flc[f]; ++fl) h.push_back(bm25_tf_host(b->k1, b->b, ix->avg[f], tf, fl));
+    off += tfc[f] * flc[f];
+  }
+  b->tab_total = off;
+  CU(b->tab.ensure(off + 1));
+  CU(cudaMemcpyAsync(b->tab.p, h.data(), off * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CU(cudaStreamSynchronize(b->stream));   // h goes out of scope
+  return PB_OK;
+}
+
+int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
+  pb_index* ix = b->ix;
+  if (!d || (d->n_queries && (!d->query_term_off || !d->term_byte_off))) { pb::set_error("query batch: null argument"); return PB_ERR_INVALID; }
+  if (d->scorer != PB_SCORER_BM25 && d->scorer != PB_SCORER_ZERO_TO_ONE) {
+    pb::set_error("query batch: scorer %u cannot run on the device (only BM25 and ZeroToOne exist there; there is no CPU fallback)", d->scorer);
+    return PB_ERR_UNSUPPORTED;
+  }
+  if (d->top_k > PB_MAX_TOP_K) { pb::set_error("query batch: top_k %u > %u", d->top_k, PB_MAX_TOP_K); return PB_ERR_UNSUPPORTED; }
+  if (d->n_fields_boost != ix->F || !d->fields_boost) { pb::set_error("query batch: fields_boost must have %u entries", ix->F); return PB_ERR_INVALID; }
+  for (uint32_t f = 0; f < ix->F; ++f)
+    if (!std::isfinite(d->fields_boost[f])) { pb::set_error("query batch: fields_boost[%u] is not finite", f); return PB_ERR_INVALID; }
+  if (d->n_queries >= 0xFFFFFFF0ull) { pb::set_error("query batch: too many queries"); return PB_ERR_UNSUPPORTED; }
+  const uint64_t Q = d->n_queries;
+  const uint64_t NT = Q ? d->query_term_off[Q] : 0;
+  if (Q && d->query_term_off[0] != 0) { pb::set_error("query batch: query_term_off[0] != 0"); return PB_ERR_INVALID; }
+  for (uint64_t q = 0; q < Q; ++q) {
+    if (d->query_term_off[q + 1] < d->query_term_off[q]) { pb::set_error("query batch: query_term_off not monotone"); return PB_ERR_INVALID; }
+    if (d->query_term_off[q + 1] - d->query_term_off[q] > PB_MAX_QUERY_TERMS) { pb::set_error("query %llu has more than %u terms", (ull)q, PB_MAX_QUERY_TERMS); return PB_ERR_UNSUPPORTED; }
+  }
+  if (NT && d->term_byte_off[0] != 0) { pb::set_error("query batch: term_byte_off[0] != 0"); return PB_ERR_INVALID; }
+  for (uint64_t t = 0; t < NT; ++t) {
+    if (d->term_byte_off[t + 1] < d->term_byte_off[t]) { pb::set_error("query batch: term_byte_off not monotone"); return PB_ERR_INVALID; }
+    if (!pb::utf8_valid(d->term_bytes + d->term_byte_off[t], d->term_byte_off[t + 1] - d->term_byte_off[t])) {
+      pb::set_error("query term %llu is not valid UTF-8", (ull)t);
+      return PB_ERR_INVALID;
+    }
+  }
+  const uint64_t NB = NT ? d->term_byte_off[NT] : 0;
+  CU(cudaSetDevice(ix->device));
+  b->Q = Q; b->NT = NT; b->scorer = d->scorer; b->k = d->top_k; b->k1 = d->bm25_k1; b->b = d->bm25_b;
+  for (uint32_t f = 0; f < 4; ++f) b->boost[f] = f < ix->F ? d->fields_boost[f] : 0.0;
+  b->full_cap = full_cap;
+  // inputs -> device (async on the batch stream; pinned sources overlap, pageable ones stage)
+  CU(b->term_bytes.ensure(NB + 16));
+  CU(b->term_byte_off.ensure(NT + 2));
+  CU(b->query_term_off.ensure(Q + 2));
+  if (NB) CU(cudaMemcpyAsync(b->term_bytes.p, d->term_bytes, NB, cudaMemcpyHostToDevice, b->stream));
+  if (NT) CU(cudaMemcpyAsync(b->term_byte_off.p, d->term_byte_off, (NT + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
+  else CU(cudaMemsetAsync(b->term_byte_off.p, 0, sizeof(uint64_t), b->stream));
+  if (Q) CU(cudaMemcpyAsync(b->query_term_off.p, d->query_term_off, (Q + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
+  else CU(cudaMemsetAsync(b->query_term_off.p, 0, sizeof(uint64_t), b->stream));
+  // workspace that depends only on Q / NT
+  CU(b->qt_lo.ensure(NT + 1)); CU(b->qt_hi.ensure(NT + 1)); CU(b->qt_len.ensure(NT + 1)); CU(b->qt_q.ensure(NT + 1));
+  CU(b->qt_gcount.ensure(NT + 2)); CU(b->qt_goff.ensure(NT + 2));
+  CU(b->q_isg.ensure(Q + 2)); CU(b->q_gidx.ensure(Q + 2)); CU(b->q_grows.ensure(Q + 2)); CU(b->q_prim.ensure(Q + 2));
+  CU(b->q_recbound.ensure(Q + 2)); CU(b->q_recoff.ensure(Q + 2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
+  CU(b->s_tiles.ensure(Q + 2)); CU(b->s_tile_off.ensure(Q + 2));
+  CU(b->seg_s.ensure(Q + 1));
+  CU(b->n_results.ensure(Q + 1)); CU(b->doc_digest.ensure(Q + 1)); CU(b->score_digest.ensure(Q + 1));
+  CU(b->topk_n.ensure(Q + 1));
+  CU(b->topk_doc.ensure(Q * std::max<uint32_t>(b->k, 1) + 1));
+  CU(b->topk_score.ensure(Q * std::max<uint32_t>(b->k, 1) + 1));
+  CU(b->part_head.ensure(Q + 1));
+  CU(b->counters.ensure(8));
+  CU(b->stats.ensure(2 * ST_COUNT));
+  if (full_cap) {
+    CU(b->full_q.ensure(full_cap)); CU(b->full_doc.ensure(full_cap)); CU(b->full_score.ensure(full_cap));
+  }
+  CU(b->full_count.ensure(2));
+  if (b->scorer == PB_SCORER_BM25) RC(batch_build_table(b));
+  CU(cudaStreamSynchronize(b->stream));   // caller buffers may be reused after return
+  b->loaded = true;
+  b->ran = false;
+  return PB_OK;
+}
+
+template <int F, int SC, bool G>
+int launch_score_t(pb_batch* b, const ScoreParams& P, int grid) {
+  size_t smem = SC == 0 ? (size_t)P.tab_total * sizeof(double) : 0;
+  score_kernel<F, SC, G><<<grid, CTA_THREADS, smem, b->stream>>>(P);
+  CU(cudaGetLastError());
+  return PB_OK;
+}
+template <int F, int SC, bool G>
+int occupancy_score_t(int* per_sm, size_t smem) {
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G>, CTA_THREADS, smem));
+  return PB_OK;
+}
+
+template <int V> using IC = std::integral_constant<int, V>;
+
+// run fn(IC<F>, IC<SCORER>) for the runtime (field count, scorer) pair
+template <class Fn>
+int dispatch_fs(uint32_t F, uint32_t scorer, Fn&& fn) {
+  switch (F * 2 + scorer) {
+    case 2: return fn(IC<1>{}, IC<0>{});
+    case 3: return fn(IC<1>{}, IC<1>{});
+    case 4: return fn(IC<2>{}, IC<0>{});
+    case 5: return fn(IC<2>{}, IC<1>{});
+    case 6: return fn(IC<3>{}, IC<0>{});
+    case 7: return fn(IC<3>{}, IC<1>{});
+    case 8: return fn(IC<4>{}, IC<0>{});
+    case 9: return fn(IC<4>{}, IC<1>{});
+    default: pb::set_error("unsupported field count / scorer"); return PB_ERR_UNSUPPORTED;
+  }
+}
+
+int launch_score(pb_batch* b, const ScoreParams& P, bool gmode, uint64_t tiles) {
+  const size_t smem = b->scorer == 0 ? (size_t)P.tab_total * sizeof(double) : 0;
+  return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
+    constexpr int F = decltype(f)::value, SC = decltype(sc)::value;
+    int per_sm = 1;
+    if (gmode) RC((occupancy_score_t<F, SC, true>(&per_sm, smem)));
+    else RC((occupancy_score_t<F, SC, false>(&per_sm, smem)));
+    if (per_sm < 1) per_sm = 1;
+    // one warp = one contiguous span of tiles; never more warps than there is work for
+    uint64_t max_grid = (uint64_t)b->ix->sm_count * per_sm;
+    uint64_t want = (tiles + WARPS_PER_CTA * 2 - 1) / (WARPS_PER_CTA * 2);
+    int grid = (int)std::max<uint64_t>(1, std::min(max_grid, want));
+    if (gmode) return launch_score_t<F, SC, true>(b, P, grid);
+    return launch_score_t<F, SC, false>(b, P, grid);
+  });
+}
+
+template <int F, int SC>
+int launch_fold_t(pb_batch* b, const FoldParams& FP, int grid) {
+  fold_kernel<F, SC><<<grid, CTA_THREADS, 0, b->stream>>>(FP);
+  CU(cudaGetLastError());
+  return PB_OK;
+}
+int launch_fold(pb_batch* b, const FoldParams& FP) {
+  uint64_t want = ((uint64_t)FP.n + CTA_THREADS - 1) / CTA_THREADS;
+  int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)b->ix->sm_count * 4, want));
+  return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
+    return launch_fold_t<decltype(f)::value, decltype(sc)::value>(b, FP, grid);
+  });
+}
+
+// Side-path capacity knobs (bytes of HBM the workspace may take).
+constexpr uint64_t REC_CAP_DEFAULT = 48ull << 20;       // records per round (x32 B with sort buffers)
+constexpr uint64_t REC_CAP_MAX = 1ull << 31;
+constexpr uint64_t BITMAP_POOL_BYTES = 1ull << 30;
+
+int batch_run(pb_batch* b) {
+  pb_index* ix = b->ix;
+  if (!b->loaded) { pb::set_error("pb_batch_run: batch not loaded"); return PB_ERR_INVALID; }
+  CU(cudaSetDevice(ix->device));
+  cudaStream_t st = b->stream;
+  const uint64_t Q = b->Q, NT = b->NT;
+  const uint32_t k = b->k;
+  pb_batch_stats& S = b->st;
+  std::memset(&S, 0, sizeof(S));
+  S.n_queries = Q; S.n_query_terms = NT;
+  uint32_t launches = 0;
+  if (ix->n_rows_padded >= 0xFFFFFFFFull) { pb::set_error("index has more than 2^32 posting rows"); return PB_ERR_UNSUPPORTED; }
+
+  CU(cudaEventRecord(b->ev[0], st));
+  CU(cudaMemsetAsync(b->n_results.p, 0, (Q + 1) * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->doc_digest.p, 0, (Q + 1) * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->score_digest.p, 0, (Q + 1) * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->topk_n.p, 0, (Q + 1) * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(b->part_head.p, 0xFF, (Q + 1) * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(b->stats.p, 0, 2 * ST_COUNT * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->q_prim.p, 0, (Q + 2) * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->full_count.p, 0, 2 * sizeof(ull), st));
+  if (Q == 0) { b->ran = true; return PB_OK; }
+
+  IndexView view = ix->view();
+  // ---- trie descent + prefix expansion ---------------------------------------------------
+  if (NT) {
+    descend_kernel<<<(unsigned)((NT + 255) / 256), 256, 0, st>>>(view, b->term_bytes.p, b->term_byte_off.p, NT,
+                                                                 b->qt_lo.p, b->qt_hi.p, b->qt_len.p);
+    CU(cudaGetLastError());
+    ++launches;
+  }
+  CU(cudaEventRecord(b->ev[1], st));
+  // ---- plan ------------------------------------------------------------------------------
+  plan_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(view, Q, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p,
+                                                                 b->qt_len.p, b->seg_s.p, b->s_tiles.p, b->qt_gcount.p,
+                                                                 b->qt_q.p, b->q_isg.p, b->q_grows.p);
+  CU(cudaGetLastError());
+  ++launches;
+  RC(scan_ull(b, b->s_tiles.p, b->s_tile_off.p, Q + 1));
+  RC(scan_ull(b, b->qt_gcount.p, b->qt_goff.p, NT + 1));
+  launches += 2;
+  ull h_tot[2] = {0, 0};
+  CU(cudaMemcpyAsync(&h_tot[0], b->s_tile_off.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&h_tot[1], b->qt_goff.p + NT, sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const ull s_tiles_total = h_tot[0], n_gsegs = h_tot[1];
+  if (n_gsegs >= 0xFFFFFFF0ull) { pb::set_error("batch expands to more than 2^32 posting lists"); return PB_ERR_UNSUPPORTED; }
+  S.n_segments = n_gsegs;   // class-S segments are added below from the stats
+
+  struct Round { uint64_t qa, qb, sa, sb, ta, tb, slots, recs; };
+  std::vector<Round> rounds;
+  const uint32_t doc_bits = bits_for(std::max<uint64_t>(ix->n_docs, 2));
+  const uint32_t bitmap_words = (uint32_t)((ix->n_docs + 31) / 32 + 1);
+  uint64_t rec_cap = 0, slot_cap = 0;
+  if (n_gsegs) {
+    CU(b->seg_g.ensure(n_gsegs + 1));
+    CU(b->g_tiles.ensure(n_gsegs + 2));
+    CU(b->g_tile_off.ensure(n_gsegs + 2));
+    gfill_kernel<<<ix->sm_count * 8, 256, 0, st>>>(view, NT, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p, b->qt_len.p,
+                                                   b->qt_q.p, b->qt_gcount.p, b->qt_goff.p, b->seg_g.p, b->g_tiles.p,
+                                                   b->q_prim.p);
+    CU(cudaGetLastError());
+    gprimary_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q, b->q_isg.p, b->q_grows.p, b->q_prim.p, b->seg_g.p,
+                                                                     b->q_recbound.p, b->query_term_off.p, b->qt_goff.p,
+                                                                     b->q_gsegoff.p);
+    CU(cudaGetLastError());
+    RC(scan_ull(b, b->g_tiles.p, b->g_tile_off.p, n_gsegs + 1));
+    RC(scan_ull(b, b->q_recbound.p, b->q_recoff.p, Q + 1));
+    RC(scan_ull(b, b->q_isg.p, b->q_gidx.p, Q + 1));
+    gather_tileoff_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q + 1, b->q_gsegoff.p, b->g_tile_off.p, b->q_gtileoff.p);
+    CU(cudaGetLastError());
+    launches += 6;
+    b->h_recoff.resize(Q + 1); b->h_gidx.resize(Q + 1); b->h_gsegoff.resize(Q + 1); b->h_gtileoff.resize(Q + 1);
+    CU(cudaMemcpyAsync(b->h_recoff.data(), b->q_recoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_gidx.data(), b->q_gidx.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_gsegoff.data(), b->q_gsegoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_gtileoff.data(), b->q_gtileoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // rounds: contiguous query ranges whose record bound and bitmap slots fit the workspace
+    slot_cap = std::max<uint64_t>(1, BITMAP_POOL_BYTES / ((uint64_t)bitmap_words * 4));
+    rec_cap = REC_CAP_DEFAULT;
+    for (uint64_t q = 0; q < Q; ++q) rec_cap = std::max<uint64_t>(rec_cap, b->h_recoff[q + 1] - b->h_recoff[q]);
+    if (rec_cap > REC_CAP_MAX) { pb::set_error("a single query needs %llu side-path records (> %llu)", (ull)rec_cap, (ull)REC_CAP_MAX); return PB_ERR_UNSUPPORTED; }
+    uint64_t qa = 0;
+    while (qa < Q) {
+      // largest qb with recoff[qb]-recoff[qa] <= rec_cap and gidx[qb]-gidx[qa] <= slot_cap
+      uint64_t qb1 = std::upper_bound(b->h_recoff.begin() + qa, b->h_recoff.end(), b->h_recoff[qa] + rec_cap) - b->h_recoff.begin() - 1;
+      uint64_t qb2 = std::upper_bound(b->h_gidx.begin() + qa, b->h_gidx.end(), b->h_gidx[qa] + slot_cap) - b->h_gidx.begin() - 1;
+      uint64_t qb = std::max<uint64_t>(qa + 1, std::min(qb1, qb2));
+      Round r{qa, qb, b->h_gsegoff[qa], b->h_gsegoff[qb], b->h_gtileoff[qa], b->h_gtileoff[qb],
+              b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa]};
+      if (r.sb > r.sa) rounds.push_back(r);
+      qa = qb;
+    }
+  }
+  S.side_rounds = (uint32_t)rounds.size();
+
+  // partial top-k lists: <= 2 per warp per launch + 2 per class-G query
+  const uint64_t max_warps = (uint64_t)ix->sm_count * 8 * WARPS_PER_CTA;
+  const uint64_t n_gq = n_gsegs ? b->h_gidx[Q] : 0;
+  const uint64_t part_cap = 2 * max_warps * (1 + 2 * rounds.size()) + 2 * n_gq + 64;
+  if (part_cap >= 0xFFFFFFF0ull) { pb::set_error("too many partial lists"); return PB_ERR_UNSUPPORTED; }
+  CU(b->part_next.ensure(part_cap)); CU(b->part_n.ensure(part_cap));
+  CU(b->part_doc.ensure(part_cap * std::max<uint32_t>(k, 1)));
+  CU(b->part_score.ensure(part_cap * std::max<uint32_t>(k, 1)));
+
+  ScoreParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.ix = view;
+  P.out.n_results = b->n_results.p; P.out.doc_digest = b->doc_digest.p; P.out.score_digest = b->score_digest.p;
+  P.out.topk_n = b->topk_n.p; P.out.topk_doc = b->topk_doc.p; P.out.topk_score = b->topk_score.p; P.out.k = k;
+  P.out.part_head = b->part_head.p; P.out.part_next = b->part_next.p; P.out.part_n = b->part_n.p;
+  P.out.part_doc = b->part_doc.p; P.out.part_score = b->part_score.p; P.out.part_count = b->counters.p + 0;
+  P.out.part_cap = (uint32_t)part_cap;
+  if (b->full_cap) { P.out.full_q = b->full_q.p; P.out.full_doc = b->full_doc.p; P.out.full_score = b->full_score.p; }
+  P.out.full_count = b->full_count.p; P.out.full_cap = b->full_cap;
+  P.out.error_flag = b->counters.p + 2;
+  P.out.results_total = b->full_count.p + 1;
+  P.query_term_off = b->query_term_off.p;
+  P.k1 = b->k1; P.b = b->b; P.one_minus_b = 1.0 - b->b; P.k1_plus_1 = b->k1 + 1.0;
+  for (int f = 0; f < 4; ++f) { P.boost[f] = b->boost[f]; P.avg[f] = ix->avg[f]; P.tab_tfcap[f] = b->tab_tfcap[f]; P.tab_flcap[f] = b->tab_flcap[f]; P.tab_off[f] = b->tab_off[f]; }
+  P.tab = b->tab.p; P.tab_total = b->scorer == 0 ? b->tab_total : 0;
+  P.doc_bits = doc_bits; P.bitmap_words = bitmap_words;
+  P.rec_count = b->counters.p + 1;
+  CU(cudaEventRecord(b->ev[2], st));
+
+  // ---- class S: every single-list query in ONE launch of the scoring kernel --------------
+  if (s_tiles_total) {
+    P.segs = b->seg_s.p; P.tile_off = (const uint64_t*)b->s_tile_off.p;
+    P.seg_begin = 0; P.seg_end = (uint32_t)Q; P.tile_begin = 0; P.tile_end = s_tiles_total;
+    P.stats = b->stats.p;
+    RC(launch_score(b, P, false, s_tiles_total));
+    ++launches;
+    S.score_launches = 1;
+  }
+  CU(cudaEventRecord(b->ev[3], st));
+
+  // ---- class G: rounds of the side path --------------------------------------------------
+  if (!rounds.empty()) {
+    uint64_t max_slots = 0;
+    for (auto& r : rounds) max_slots = std::max(max_slots, r.slots);
+    const size_t bm_words_total = (size_t)max_slots * bitmap_words;
+    CU(b->bitmap.ensure(bm_words_total + 1));
+    if (b->bitmap_zeroed < b->bitmap.cap) {      // freshly (re)allocated: zero once; rounds clean up after themselves
+      CU(cudaMemsetAsync(b->bitmap.p, 0, b->bitmap.cap * sizeof(uint32_t), st));
+      b->bitmap_zeroed = b->bitmap.cap;
+    }
+    CU(b->rec_key.ensure(rec_cap)); CU(b->rec_val.ensure(rec_cap));
+    CU(b->rec_key2.ensure(rec_cap)); CU(b->rec_val2.ensure(rec_cap));
+    P.segs = b->seg_g.p; P.tile_off = (const uint64_t*)b->g_tile_off.p;
+    P.bitmap = b->bitmap.p;
+    P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)rec_cap;
+    P.stats = b->stats.p + ST_COUNT;
+    for (auto& r : rounds) {
+      P.seg_begin = (uint32_t)r.sa; P.seg_end = (uint32_t)r.sb; P.tile_begin = r.ta; P.tile_end = r.tb;
+      const uint64_t nseg = r.sb - r.sa, tiles = r.tb - r.ta;
+      gslot_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, (uint32_t)r.qa);
+      CU(cudaGetLastError());
+      int mgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * 8, (tiles + 15) / 16));
+      mark_kernel<<<mgrid, CTA_THREADS, 0, st>>>(P, 0);
+      CU(cudaGetLastError());
+      RC(launch_score(b, P, true, tiles));
+      launches += 3;
+      uint32_t h_rec = 0;
+      CU(cudaMemcpyAsync(&h_rec, b->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (h_rec > rec_cap) { pb::set_error("side-path record buffer overflow (%u > %llu)", h_rec, (ull)rec_cap); return PB_ERR_INVALID; }
+      if (h_rec) {
+        const int end_bit = (int)std::min<uint32_t>(64, doc_bits + bits_for(std::max<uint64_t>(r.slots, 2)));
+        size_t bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, b->rec_key.p, b->rec_key2.p, b->rec_val.p, b->rec_val2.p,
+                                           (int64_t)h_rec, 0, end_bit, st));
+        CU(b->cub_temp.ensure(bytes));
+        bytes = b->cub_temp.cap;
+        CU(cub::DeviceRadixSort::SortPairs(b->cub_temp.p, bytes, b->rec_key.p, b->rec_key2.p, b->rec_val.p, b->rec_val2.p,
+                                           (int64_t)h_rec, 0, end_bit, st));
+        FoldParams FP;
+        FP.S = P; FP.key = b->rec_key2.p; FP.val = b->rec_val2.p; FP.n = h_rec;
+        RC(launch_fold(b, FP));
+        launches += 2 + (uint32_t)((end_bit + 7) / 8);
+      }
+      mark_kernel<<<mgrid, CTA_THREADS, 0, st>>>(P, 1);
+      CU(cudaGetLastError());
+      ++launches;
+      CU(cudaMemsetAsync(b->counters.p + 1, 0, sizeof(uint32_t), st));
+    }
+  }
+  CU(cudaEventRecord(b->ev[4], st));
+
+  // ---- finalize: merge partial top-k lists -----------------------------------------------
+  if (k) {
+    uint64_t want = (Q + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * 8, want));
+    finalize_kernel<<<grid, CTA_THREADS, 0, st>>>(P.out, Q);
+    CU(cudaGetLastError());
+    ++launches;
+  }
+  CU(cudaEventRecord(b->ev[5], st));
+  ull h_stats[2 * ST_COUNT];
+  uint32_t h_cnt[4] = {0, 0, 0, 0};
+  ull h_full[2] = {0, 0};
+  CU(cudaMemcpyAsync(h_full, b->full_count.p, sizeof(h_full), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_stats, b->stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_cnt, b->counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (h_cnt[2] & 1u) { pb::set_error("internal: partial top-k list overflow"); return PB_ERR_INVALID; }
+  if (h_cnt[2] & 2u) { pb::set_error("internal: side-path record buffer overflow"); return PB_ERR_INVALID; }
+  if (h_cnt[2] & 4u) { pb::set_error("a document received more than 64 (query term, expansion) events in one ZeroToOne query"); return PB_ERR_UNSUPPORTED; }
+  S.rows_streamed = h_stats[ST_ROWS_STREAMED] + h_stats[ST_COUNT + ST_ROWS_STREAMED];
+  S.rows_scored = h_stats[ST_ROWS_SCORED] + h_stats[ST_COUNT + ST_ROWS_SCORED];
+  S.pointer_visits = h_stats[ST_POINTER_VISITS] + h_stats[ST_COUNT + ST_POINTER_VISITS];
+  S.rows_diverted = h_stats[ST_COUNT + ST_ROWS_DIVERTED];
+  S.rows_streamed_direct = h_stats[ST_ROWS_STREAMED];
+  S.results_emitted = h_full[1];
+  S.gpu_launches = launches;
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, b->ev[0], b->ev[5])); S.ms_total = ms;
+  CU(cudaEventElapsedTime(&ms, b->ev[0], b->ev[1])); S.ms_descend = ms;
+  CU(cudaEventElapsedTime(&ms, b->ev[1], b->ev[2])); S.ms_plan = ms;
+  CU(cudaEventElapsedTime(&ms, b->ev[2], b->ev[3])); S.ms_score = ms;
+  CU(cudaEventElapsedTime(&ms, b->ev[3], b->ev[4])); S.ms_side = ms;
+  CU(cudaEventElapsedTime(&ms, b->ev[4], b->ev[5])); S.ms_finalize = ms;
+  b->ran = true;
+  return PB_OK;
+}
+
+int batch_new(pb_index* ix, pb_batch** out) {
+  CU(cudaSetDevice(ix->device));
+  pb_batch* b = new pb_batch();
+  b->ix = ix;
+  cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->ev[i]);
+  if (e != cudaSuccess) { delete b; pb::set_error("stream/event creation failed: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+  *out = b;
+  return PB_OK;
+}
+
+int batch_fetch(pb_batch* b, pb_query_results* o) {
+  if (!b->ran) { pb::set_error("pb_batch_fetch: batch has not been run"); return PB_ERR_INVALID; }
+  CU(cudaSetDevice(b->ix->device));
+  const uint64_t Q = b->Q;
+  cudaStream_t st = b->stream;
+  if (Q) {
+    if (o->n_results) CU(cudaMemcpyAsync(o->n_results, b->n_results.p, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if (o->doc_digest) CU(cudaMemcpyAsync(o->doc_digest, b->doc_digest.p, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if (o->score_digest) CU(cudaMemcpyAsync(o->score_digest, b->score_digest.p, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if (o->topk_n) CU(cudaMemcpyAsync(o->topk_n, b->topk_n.p, Q * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (b->k && o->topk_doc) CU(cudaMemcpyAsync(o->topk_doc, b->topk_doc.p, Q * b->k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (b->k && o->topk_score) CU(cudaMemcpyAsync(o->topk_score, b->topk_score.p, Q * b->k * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  return PB_OK;
+}
+
+int index_scratch(pb_index* ix, pb_batch** out) {
+  if (!ix->scratch) RC(batch_new(ix, &ix->scratch));
+  *out = ix->scratch;
+  return PB_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int pb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
+  if (!im || !out) { pb::set_error("pb_index_create: null argument"); return PB_ERR_INVALID; }
+  if (im->version != 1 || im->num_fields == 0 || im->num_fields > PB_MAX_FIELDS) { pb::set_error("pb_index_create: bad image header"); return PB_ERR_INVALID; }
+  if (im->n_rows_padded % TILE_ROWS != 0 || im->n_rows_padded < im->n_rows + TILE_ROWS) { pb::set_error("pb_index_create: posting columns must be padded to whole 128-row tiles plus one spare tile"); return PB_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    pb::set_error("no CUDA device is available (%s); this library has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    return PB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { pb::set_error("pb_index_create: device %d out of range (0..%d)", device, ndev - 1); return PB_ERR_INVALID; }
+  PB_TRY({
+    CU(cudaSetDevice(device));
+    pb_index* ix = new pb_index();
+    std::unique_ptr<pb_index> guard(ix);
+    ix->device = device; ix->sm_count = g_sm_count(device);
+    ix->F = im->num_fields;
+    ix->n_nodes = im->n_nodes; ix->n_edges = im->n_edges; ix->n_terms = im->n_terms;
+    ix->n_rows = im->n_rows; ix->n_rows_padded = im->n_rows_padded; ix->n_docs = im->n_docs;
+    ix->max_term_bytes = im->max_term_bytes;
+    for (uint32_t f = 0; f < ix->F; ++f) { ix->max_tf[f] = im->max_tf[f]; ix->max_fl[f] = im->max_fl[f]; }
+    CU(upload(ix->node_edge_begin, im->node_edge_begin, im->n_nodes + 1));
+    CU(upload(ix->node_term_lo, im->node_term_lo, im->n_nodes));
+    CU(upload(ix->node_term_hi, im->node_term_hi, im->n_nodes));
+    CU(upload(ix->edge_char, im->edge_char, im->n_edges));
+    CU(upload(ix->edge_child, im->edge_child, im->n_edges));
+    CU(upload(ix->term_row_begin, im->term_row_begin, im->n_terms + 1));
+    CU(upload(ix->term_byte_len, im->term_byte_len, im->n_terms));
+    CU(upload(ix->post_doc, im->post_doc, im->n_rows_padded, TILE_ROWS));
+    for (uint32_t f = 0; f < ix->F; ++f) {
+      CU(upload(ix->post_tf[f], im->post_tf[f], im->n_rows_padded, TILE_ROWS));
+      CU(upload(ix->post_fl[f], im->post_fl[f], im->n_rows_padded, TILE_ROWS));
+    }
+    ix->h_node_parent.assign(im->node_parent, im->node_parent + im->n_nodes);
+    ix->h_node_char.assign(im->node_char, im->node_char + im->n_nodes);
+    ix->h_term_node.assign(im->term_node, im->term_node + im->n_terms);
+    ix->h_term_row_begin.assign(im->term_row_begin, im->term_row_begin + im->n_terms + 1);
+    // expansion boost by byte-length delta, bm25.rs:45-53 (libm log on the host)
+    std::vector<double> eb(im->max_term_bytes + 2, 1.0);
+    for (size_t d = 1; d < eb.size(); ++d) eb[d] = std::log(1.0 + (1.0 / (1.0 + (double)d)));   // (1 + explen) - qlen = 1 + d exactly
+    CU(upload(ix->eb, eb.data(), eb.size()));
+    RC(index_apply_live_state(ix, im->removed_bitmap, im->n_removed, im->n_live_docs, im->field_avg));
+    *out = guard.release();
+    return PB_OK;
+  });
+}
+
+int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t n_removed, uint64_t n_live_docs,
+                            const double* field_avg) {
+  if (!ix || !field_avg || (n_removed && !removed_ords)) { pb::set_error("pb_index_set_live_state: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::vector<uint32_t> bm((ix->n_docs + 31) / 32 + 1, 0);
+    uint64_t distinct = 0;
+    for (uint64_t i = 0; i < n_removed; ++i) {
+      uint32_t d = removed_ords[i];
+      if (d >= ix->n_docs) { pb::set_error("pb_index_set_live_state: ordinal %u out of range", d); return PB_ERR_INVALID; }
+      if (!((bm[d >> 5] >> (d & 31)) & 1u)) ++distinct;
+      bm[d >> 5] |= 1u << (d & 31);
+    }
+    return index_apply_live_state(ix, bm.data(), distinct, n_live_docs, field_avg);
+  });
+}
+
+void pb_index_destroy(pb_index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  delete ix->scratch;
+  delete ix;
+}
+
+int pb_index_term_df_live(pb_index* ix, uint64_t* out, uint64_t cap) {
+  if (!ix || !out) return PB_ERR_INVALID;
+  if (cap < ix->n_terms) { pb::set_error("pb_index_term_df_live: need %llu entries", (ull)ix->n_terms); return PB_ERR_CAPACITY; }
+  for (uint64_t t = 0; t < ix->n_terms; ++t) out[t] = ix->h_df_live[t];
+  return PB_OK;
+}
+
+int pb_index_expand_term(pb_index* ix, const uint8_t* term, uint64_t term_len, uint8_t* out, uint64_t cap,
+                         uint64_t* n_expansions, uint64_t* needed) {
+  if (!ix || !n_expansions || !needed || (term_len && !term)) { pb::set_error("pb_index_expand_term: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *n_expansions = 0; *needed = 0;
+    if (!pb::utf8_valid(term, term_len)) { pb::set_error("pb_index_expand_term: invalid UTF-8"); return PB_ERR_INVALID; }
+    pb_batch* b = nullptr;
+    RC(index_scratch(ix, &b));
+    CU(cudaSetDevice(ix->device));
+    uint64_t off[2] = {0, term_len};
+    CU(b->term_bytes.ensure(term_len + 16)); CU(b->term_byte_off.ensure(3));
+    CU(b->qt_lo.ensure(2)); CU(b->qt_hi.ensure(2)); CU(b->qt_len.ensure(2));
+    if (term_len) CU(cudaMemcpyAsync(b->term_bytes.p, term, term_len, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->term_byte_off.p, off, sizeof(off), cudaMemcpyHostToDevice, b->stream));
+    b->loaded = false;
+    descend_kernel<<<1, 32, 0, b->stream>>>(ix->view(), b->term_bytes.p, b->term_byte_off.p, 1, b->qt_lo.p, b->qt_hi.p, b->qt_len.p);
+    CU(cudaGetLastError());
+    uint32_t lo = 0, hi = 0;
+    CU(cudaMemcpyAsync(&lo, b->qt_lo.p, 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(&hi, b->qt_hi.p, 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    // the device kernel skips empty tokens (query.rs:35); expand_term("") itself expands the root
+    if (term_len == 0) { lo = 0; hi = (uint32_t)ix->n_terms; }
+    uint64_t pos = 0;
+    std::string s;
+    for (uint32_t t = lo; t < hi; ++t) {
+      s.clear();
+      std::vector<uint32_t> cps;
+      for (uint32_t n = ix->h_term_node[t]; n != 0 && n != NONE; n = ix->h_node_parent[n]) cps.push_back(ix->h_node_char[n]);
+      for (size_t i = cps.size(); i-- > 0;) {
+        uint32_t c = cps[i];
+        if (c < 0x80) s.push_back((char)c);
+        else if (c < 0x800) { s.push_back((char)(0xC0 | (c >> 6))); s.push_back((char)(0x80 | (c & 0x3F))); }
+        else if (c < 0x10000) { s.push_back((char)(0xE0 | (c >> 12))); s.push_back((char)(0x80 | ((c >> 6) & 0x3F))); s.push_back((char)(0x80 | (c & 0x3F))); }
+        else { s.push_back((char)(0xF0 | (c >> 18))); s.push_back((char)(0x80 | ((c >> 12) & 0x3F))); s.push_back((char)(0x80 | ((c >> 6) & 0x3F))); s.push_back((char)(0x80 | (c & 0x3F))); }
+      }
+      if (t > lo) { if (pos < cap && out) out[pos] = '\n'; ++pos; }
+      for (char c : s) { if (pos < cap && out) out[pos] = (uint8_t)c; ++pos; }
+    }
+    *n_expansions = hi - lo;
+    *needed = pos;
+    return PB_OK;
+  });
+}
+
+int pb_batch_create(pb_index* ix, const pb_query_batch_desc* q, pb_batch** out) {
+  if (!ix || !q || !out) { pb::set_error("pb_batch_create: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    pb_batch* b = nullptr;
+    RC(batch_new(ix, &b));
+    int rc = batch_load(b, q, 0);
+    if (rc != PB_OK) { delete b; return rc; }
+    *out = b;
+    return PB_OK;
+  });
+}
+
+int pb_batch_run(pb_batch* b) {
+  if (!b) return PB_ERR_INVALID;
+  PB_TRY({ return batch_run(b); });
+}
+
+int pb_batch_fetch(pb_batch* b, pb_query_results* out) {
+  if (!b || !out) return PB_ERR_INVALID;
+  PB_TRY({ return batch_fetch(b, out); });
+}
+
+void pb_batch_destroy(pb_batch* b) { delete b; }
+
+int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out) {
+  if (!b || !out) return PB_ERR_INVALID;
+  *out = b->st;
+  return PB_OK;
+}
+
+int pb_query_batch(pb_index* ix, const pb_query_batch_desc* q, pb_query_results* out) {
+  if (!ix || !q || !out) { pb::set_error("pb_query_batch: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    std::lock_guard<std::mutex> lk(ix->mu);
+    pb_batch* b = nullptr;
+    RC(index_scratch(ix, &b));
+    RC(batch_load(b, q, 0));
+    RC(batch_run(b));
+    return batch_fetch(b, out);
+  });
+}
+
+int pb_index_last_stats(pb_index* ix, pb_batch_stats* out) {
+  if (!ix || !out || !ix->scratch) return PB_ERR_INVALID;
+  *out = ix->scratch->st;
+  return PB_OK;
+}
+
+int pb_query_full(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint32_t* out_query, uint32_t* out_doc,
+                  double* out_score, uint64_t* n_total) {
+  if (!ix || !q || !n_total) { pb::set_error("pb_query_full: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    std::lock_guard<std::mutex> lk(ix->mu);
+    pb_batch* b = nullptr;
+    RC(index_scratch(ix, &b));
+    pb_query_batch_desc d = *q;
+    RC(batch_load(b, &d, std::max<uint64_t>(cap, 1)));
+    int rc = batch_run(b);
+    b->full_cap = 0;
+    RC(rc);
+    ull total = 0;
+    CU(cudaMemcpy(&total, b->full_count.p, sizeof(ull), cudaMemcpyDeviceToHost));
+    *n_total = total;
+    if (total > cap) { pb::set_error("pb_query_full: %llu results, capacity %llu", total, (ull)cap); return PB_ERR_CAPACITY; }
+    if (total) {
+      if (!out_query || !out_doc || !out_score) { pb::set_error("pb_query_full: null output"); return PB_ERR_INVALID; }
+      CU(cudaMemcpy(out_query, b->full_q.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(out_doc, b->full_doc.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(out_score, b->full_score.p, total * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return PB_OK;
+  });
+}
+
+void* pb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,834 @@
+// Device code of the query hot path (sm_100a).  Everything the reference does per query in
+// src/query.rs:21-164 and src/score/default/{bm25,zero_to_one}.rs happens in these kernels.
+//
+//   descend_kernel     find_inverted_index_node (index.rs:300-337) over the CSR trie; because
+//                      nodes/terms are numbered in DFS pre-order the whole of expand_term
+//                      (query.rs:109-147) collapses to the term range [lo, hi) of the node.
+//   plan_*             per query: how many live expanded lists, which class (single list ->
+//                      streamed directly; several lists -> primary list streamed + the rest
+//                      through the sort/fold side path), segment descriptors.
+//   live_df_kernel     count_documents (index.rs:282-297) for every term at once.
+//   score_kernel       THE hot loop (query.rs:61-89): posting rows -> removed mask -> BM25 /
+//                      zero-to-one -> fused count / digest / top-k, or diversion to the side path.
+//   mark_kernel        marks docs that occur in a non-primary list of a multi-list query.
+//   fold_kernel        max_score_merger (query.rs:150-164) and ZeroToOne::finalize
+//                      (zero_to_one.rs:84-126) on docs that received several events.
+//   finalize_kernel    merges per-warp partial top-k lists (query.rs:97-105: result + sort).
+//
+// f64 arithmetic is done with __d*_rn intrinsics in the reference's operation order, so no FMA
+// contraction can change a bit (rustc never contracts).  Both logarithms of BM25 are per term
+// and are tabulated on the host with libm (engine.cu), never computed on the device.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pbk {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr int TILE_ROWS = 128;          // 32 lanes x 4 rows: one 512 B line group per column
+constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+
+enum SegMode : uint8_t { MODE_DIRECT = 0, MODE_PRIMARY = 1, MODE_SECONDARY = 2 };
+
+// One posting list walked for one (query term, expanded term): the unit query.rs:38-91 iterates.
+struct __align__(16) Seg {
+  uint64_t row_begin;
+  uint32_t n_rows;
+  uint32_t q;          // query index in the batch
+  uint32_t term;       // expanded term ordinal (DFS order)
+  uint32_t qlen;       // UTF-8 byte length of the query term
+  uint16_t qti;        // query_term_index (query.rs:34)
+  uint8_t mode;
+  uint8_t pad;
+  uint32_t slot;       // bitmap slot of the query inside its side-path round
+};
+static_assert(sizeof(Seg) == 32, "Seg layout");
+
+struct IndexView {
+  const uint32_t* node_edge_begin;
+  const uint32_t* node_term_lo;
+  const uint32_t* node_term_hi;
+  const uint32_t* edge_char;
+  const uint32_t* edge_child;
+  const uint64_t* term_row_begin;
+  const uint32_t* term_byte_len;
+  const uint32_t* post_doc;
+  const uint32_t* post_tf[4];
+  const uint32_t* post_fl[4];
+  const uint32_t* removed;        // bitmap, bit set = doc not live
+  const uint64_t* term_df_live;
+  const uint32_t* live_prefix;    // [n_terms+1] number of terms with df_live > 0 before t
+  const uint64_t* liverows_prefix;// [n_terms+1] rows of live terms before t
+  const double* term_idf;         // bm25.rs:56, host libm
+  const double* eb;               // bm25.rs:45-53 by byte-length delta, host libm
+  uint32_t n_terms;
+  uint32_t n_docs;
+  uint32_t num_fields;
+  uint32_t has_removed;
+};
+
+struct Outputs {
+  unsigned long long* n_results;
+  unsigned long long* doc_digest;
+  unsigned long long* score_digest;
+  uint32_t* topk_n;
+  uint32_t* topk_doc;
+  double* topk_score;
+  uint32_t k;
+  // partial top-k lists (queries whose rows were handled by more than one warp / kernel)
+  uint32_t* part_head;   // [n_queries]
+  uint32_t* part_next;
+  uint32_t* part_n;
+  uint32_t* part_doc;    // [part_cap * k]
+  double* part_score;
+  uint32_t* part_count;
+  uint32_t part_cap;
+  // full result capture (pb_query_full)
+  uint32_t* full_q;
+  uint32_t* full_doc;
+  double* full_score;
+  unsigned long long* full_count;
+  unsigned long long full_cap;
+  uint32_t* error_flag;  // bit 0: partial list overflow, bit 1: record buffer overflow
+  unsigned long long* results_total;   // sum of n_results over the batch
+};
+
+enum StatSlot { ST_ROWS_STREAMED = 0, ST_ROWS_SCORED, ST_POINTER_VISITS, ST_ROWS_DIVERTED, ST_COUNT };
+
+struct ScoreParams {
+  IndexView ix;
+  Outputs out;
+  const Seg* segs;
+  const uint64_t* tile_off;      // exclusive prefix of tiles per segment, [n_segs + 1], absolute
+  uint32_t seg_begin, seg_end;   // segment range of this launch
+  uint64_t tile_begin, tile_end; // = tile_off[seg_begin], tile_off[seg_end]
+  const uint64_t* query_term_off;// query_terms_len = off[q+1]-off[q] (query.rs:32)
+  // BM25
+  double k1, b, one_minus_b, k1_plus_1;
+  double boost[4];
+  double avg[4];
+  const double* tab;             // [F][tfcap][flcap] saturated tf (bm25.rs:78-82), host-computed
+  uint32_t tab_tfcap[4], tab_flcap[4], tab_off[4], tab_total;
+  // side path
+  uint32_t* bitmap;              // [slots][bitmap_words]
+  uint32_t bitmap_words;
+  unsigned long long* rec_key;
+  unsigned long long* rec_val;
+  uint32_t* rec_count;
+  uint32_t rec_cap;
+  uint32_t doc_bits;
+  unsigned long long* stats;     // [ST_COUNT]
+};
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint64_t doc_hash(uint32_t doc) {
+  uint64_t x = (uint64_t(doc) + 1ull) * 0x9E3779B97F4A7C15ull;
+  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+  return x;
+}
+__device__ __forceinline__ uint64_t score_hash(uint64_t dh, double s) {
+  uint64_t y = (dh ^ (uint64_t)__double_as_longlong(s)) * 0xD6E8FEB86659FD93ull;
+  y ^= y >> 32;
+  return y;
+}
+
+__device__ __forceinline__ bool better(double as, uint32_t ad, double bs, uint32_t bd) {
+  return as > bs || (as == bs && ad < bd);     // (score desc, doc asc), src/lib.rs:54-58
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, o);
+    uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), o);
+    v += (uint64_t(hi) << 32) | lo;
+  }
+  return v;
+}
+
+// BM25 saturated term frequency, bm25.rs:78-82, in the reference's operation order.
+__device__ __forceinline__ double bm25_tf_slow(const ScoreParams& P, uint32_t tf, uint32_t fl, int f) {
+  double tfd = (double)tf;
+  double num = __dmul_rn(P.k1_plus_1, tfd);
+  double ratio = __ddiv_rn((double)fl, P.avg[f]);
+  double inner = __dadd_rn(P.one_minus_b, __dmul_rn(P.b, ratio));
+  double den = __dadd_rn(__dmul_rn(P.k1, inner), tfd);
+  return __ddiv_rn(num, den);
+}
+
+// zero_to_one.rs:72 — 1 - |explen - qlen| / explen  (byte lengths)
+__device__ __forceinline__ double z2o_term_score(uint32_t explen, uint32_t qlen) {
+  double e = (double)explen, q = (double)qlen;
+  return __dsub_rn(1.0, __ddiv_rn(fabs(__dsub_rn(e, q)), e));
+}
+// zero_to_one.rs:117-120 — min(s/tf, 1) * tf / max(field_length, query_terms_len)
+__device__ __forceinline__ double z2o_entry(double s, uint32_t tf, uint32_t fl, uint32_t qtl) {
+  double tfd = (double)tf;
+  double v = __dmul_rn(fmin(__ddiv_rn(s, tfd), 1.0), tfd);
+  return __ddiv_rn(v, (double)max(fl, qtl));
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-warp result accumulator: count, digests, and a top-32 kept sorted across the lanes
+// (lane i holds the i-th best).  One accumulator follows one query at a time.
+// ------------------------------------------------------------------------------------------
+struct WarpAcc {
+  uint32_t q;
+  uint32_t cnt;          // per lane
+  uint64_t dd, sd;       // per lane
+  double ts; uint32_t td;
+  double thr_s; uint32_t thr_d;
+
+  __device__ __forceinline__ void reset(uint32_t nq) {
+    q = nq; cnt = 0; dd = 0; sd = 0;
+    ts = -1.0; td = NONE; thr_s = -1.0; thr_d = NONE;
+  }
+
+  __device__ __forceinline__ void insert_candidates(bool c, uint32_t doc, double s, int lane, int k) {
+    uint32_t m = __ballot_sync(0xffffffffu, c);
+    while (m) {
+      int l = __ffs(m) - 1;
+      m &= m - 1;
+      double cs = __shfl_sync(0xffffffffu, s, l);
+      uint32_t cd = __shfl_sync(0xffffffffu, doc, l);
+      if (!better(cs, cd, thr_s, thr_d)) continue;     // warp-uniform
+      int pos = __popc(__ballot_sync(0xffffffffu, better(ts, td, cs, cd)));
+      double us = __shfl_up_sync(0xffffffffu, ts, 1);
+      uint32_t ud = __shfl_up_sync(0xffffffffu, td, 1);
+      if (lane > pos) { ts = us; td = ud; }
+      else if (lane == pos) { ts = cs; td = cd; }
+      thr_s = __shfl_sync(0xffffffffu, ts, k - 1);
+      thr_d = __shfl_sync(0xffffffffu, td, k - 1);
+    }
+  }
+
+  __device__ __forceinline__ void add(const Outputs& o, bool valid, uint32_t doc, double s, int lane) {
+    if (valid) {
+      ++cnt;
+      uint64_t h = doc_hash(doc);
+      dd += h;
+      sd += score_hash(h, s);
+    }
+    if (o.full_q) {
+      uint32_t m = __ballot_sync(0xffffffffu, valid);
+      if (m) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(o.full_count, (unsigned long long)__popc(m));
+        base = shfl_u64(base, 0);
+        unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+        if (valid && pos < o.full_cap) { o.full_q[pos] = q; o.full_doc[pos] = doc; o.full_score[pos] = s; }
+      }
+    }
+    if (o.k) insert_candidates(valid && better(s, doc, thr_s, thr_d), doc, s, lane, (int)o.k);
+  }
+
+  // owned: this warp saw every row of the query, so it may write the final top-k itself.
+  __device__ __forceinline__ void flush(const Outputs& o, bool owned, int lane) {
+    uint32_t total = cnt;
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) total += __shfl_xor_sync(0xffffffffu, total, of);
+    if (total == 0) return;
+    uint64_t tdd = warp_sum_u64(dd), tsd = warp_sum_u64(sd);
+    if (lane == 0) {
+      atomicAdd(&o.n_results[q], (unsigned long long)total);
+      atomicAdd(&o.doc_digest[q], (unsigned long long)tdd);
+      atomicAdd(&o.score_digest[q], (unsigned long long)tsd);
+      atomicAdd(o.results_total, (unsigned long long)total);
+    }
+    if (o.k == 0) return;
+    uint32_t ntop = min(min(total, 32u), o.k);
+    if (owned) {
+      if (lane < (int)ntop) {
+        o.topk_doc[(size_t)q * o.k + lane] = td;
+        o.topk_score[(size_t)q * o.k + lane] = ts;
+      }
+      if (lane == 0) o.topk_n[q] = ntop;
+    } else {
+      uint32_t slot = 0;
+      if (lane == 0) slot = atomicAdd(o.part_count, 1u);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot >= o.part_cap) {
+        if (lane == 0) atomicOr(o.error_flag, 1u);
+        return;
+      }
+      if (lane < (int)ntop) {
+        o.part_doc[(size_t)slot * o.k + lane] = td;
+        o.part_score[(size_t)slot * o.k + lane] = ts;
+      }
+      if (lane == 0) {
+        o.part_n[slot] = ntop;
+        o.part_next[slot] = atomicExch(&o.part_head[q], slot);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Trie descent + prefix expansion
+// ------------------------------------------------------------------------------------------
+// One thread per query term.  find_inverted_index_node (index.rs:300-318) with a binary search
+// over the node's char-sorted edges instead of the sibling-list scan (index.rs:321-337).
+// Output: the DFS term range [lo, hi) = expand_term's result (query.rs:109-147), already in the
+// reference's expansion order; lo == hi when nothing matches or the token is empty (query.rs:35).
+__global__ void descend_kernel(IndexView ix, const uint8_t* __restrict__ term_bytes,
+                               const uint64_t* __restrict__ term_byte_off, uint64_t n_qterms,
+                               uint32_t* __restrict__ qt_lo, uint32_t* __restrict__ qt_hi,
+                               uint32_t* __restrict__ qt_len) {
+  uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= n_qterms) return;
+  const uint8_t* p = term_bytes + term_byte_off[t];
+  const uint8_t* e = term_bytes + term_byte_off[t + 1];
+  uint32_t len = (uint32_t)(e - p);
+  qt_len[t] = len;
+  uint32_t node = 0;
+  bool ok = len > 0;
+  while (ok && p < e) {
+    uint32_t c = *p++;
+    if (c >= 0x80) {                       // UTF-8 (validated on the host) -> Unicode scalar
+      int extra = (c >= 0xF0) ? 3 : (c >= 0xE0) ? 2 : 1;
+      c &= (0x3Fu >> extra);
+      for (int i = 0; i < extra && p < e; ++i) c = (c << 6) | (*p++ & 0x3Fu);
+    }
+    uint32_t lo = ix.node_edge_begin[node], hi = ix.node_edge_begin[node + 1];
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (ix.edge_char[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    if (lo < ix.node_edge_begin[node + 1] && ix.edge_char[lo] == c) node = ix.edge_child[lo];
+    else ok = false;
+  }
+  qt_lo[t] = ok ? ix.node_term_lo[node] : 0u;
+  qt_hi[t] = ok ? ix.node_term_hi[node] : 0u;
+}
+
+// count_documents (index.rs:282-297) for every term: live occurrence count
+// df_live(t) = sum over the term's rows whose doc is live of sum_x tf[x]  (SURVEY §3.4 rule 2).
+template <int F>
+__global__ void live_df_kernel(IndexView ix, unsigned long long* __restrict__ df_live) {
+  int lane = threadIdx.x & 31;
+  uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = warp; t < ix.n_terms; t += nwarps) {
+    uint64_t a = ix.term_row_begin[t], b = ix.term_row_begin[t + 1];
+    unsigned long long s = 0;
+    for (uint64_t r = a + lane; r < b; r += 32) {
+      uint32_t d = ix.post_doc[r];
+      bool live = !((ix.removed[d >> 5] >> (d & 31)) & 1u);
+      if (live) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) s += ix.post_tf[f][r];
+      }
+    }
+    s = warp_sum_u64(s);
+    if (lane == 0) df_live[t] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Planning
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t first_live_term(const IndexView& ix, uint32_t lo, uint32_t hi) {
+  // smallest t in [lo, hi) with df_live > 0, i.e. live_prefix[t+1] > live_prefix[lo]
+  uint32_t base = ix.live_prefix[lo];
+  uint32_t a = lo, b = hi;
+  while (a < b) {
+    uint32_t mid = (a + b) >> 1;
+    if (ix.live_prefix[mid + 1] > base) b = mid; else a = mid + 1;
+  }
+  return a;
+}
+
+// One thread per query.  Classifies the query by the number of live posting lists its terms
+// expand to (terms whose live df is 0 are skipped, query.rs:48):
+//   0 lists  -> empty result          1 list -> class S: one DIRECT segment (seg_s[q])
+//   >= 2     -> class G: qt_gcount[t] segments per query term, filled by gfill_kernel.
+__global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
+                                  const uint64_t* __restrict__ query_term_off,
+                                  const uint32_t* __restrict__ qt_lo, const uint32_t* __restrict__ qt_hi,
+                                  const uint32_t* __restrict__ qt_len, Seg* __restrict__ seg_s,
+                                  unsigned long long* __restrict__ s_tiles, unsigned long long* __restrict__ qt_gcount,
+                                  uint32_t* __restrict__ qt_q, unsigned long long* __restrict__ q_isg,
+                                  unsigned long long* __restrict__ q_grows) {
+  uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  uint64_t t0 = query_term_off[q], t1 = query_term_off[q + 1];
+  uint32_t nl = 0;
+  uint64_t rows = 0;
+  uint64_t single = t0;
+  for (uint64_t t = t0; t < t1; ++t) {
+    uint32_t lo = qt_lo[t], hi = qt_hi[t];
+    uint32_t c = ix.live_prefix[hi] - ix.live_prefix[lo];
+    if (c) single = t;
+    nl += c;
+    rows += ix.liverows_prefix[hi] - ix.liverows_prefix[lo];
+    qt_q[t] = (uint32_t)q;
+  }
+  Seg s;
+  s.row_begin = 0; s.n_rows = 0; s.q = (uint32_t)q; s.term = 0; s.qlen = 0; s.qti = 0;
+  s.mode = MODE_DIRECT; s.pad = 0; s.slot = 0;
+  unsigned long long tiles = 0;
+  if (nl == 1) {
+    uint32_t term = first_live_term(ix, qt_lo[single], qt_hi[single]);
+    uint64_t a = ix.term_row_begin[term], b = ix.term_row_begin[term + 1];
+    s.row_begin = a; s.n_rows = (uint32_t)(b - a); s.term = term; s.qlen = qt_len[single];
+    s.qti = (uint16_t)(single - t0);
+    tiles = ((b + TILE_ROWS - 1) / TILE_ROWS) - (a / TILE_ROWS);
+  }
+  seg_s[q] = s;
+  s_tiles[q] = tiles;
+  bool g = nl >= 2;
+  q_isg[q] = g ? 1ull : 0ull;
+  q_grows[q] = g ? rows : 0ull;
+  for (uint64_t t = t0; t < t1; ++t)
+    qt_gcount[t] = g ? (unsigned long long)(ix.live_prefix[qt_hi[t]] - ix.live_prefix[qt_lo[t]]) : 0ull;
+}
+
+// One warp per query term of a class-G query: writes one SECONDARY segment per live expanded
+// term, in expansion order, and elects the query's largest list (atomicMax on rows<<32|seg).
+__global__ void gfill_kernel(IndexView ix, uint64_t n_qterms, const uint64_t* __restrict__ query_term_off,
+                             const uint32_t* __restrict__ qt_lo, const uint32_t* __restrict__ qt_hi,
+                             const uint32_t* __restrict__ qt_len, const uint32_t* __restrict__ qt_q,
+                             const unsigned long long* __restrict__ qt_gcount, const unsigned long long* __restrict__ qt_goff,
+                             Seg* __restrict__ seg_g, unsigned long long* __restrict__ g_tiles,
+                             unsigned long long* __restrict__ q_prim) {
+  int lane = threadIdx.x & 31;
+  uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = warp; t < n_qterms; t += nwarps) {
+    if (qt_gcount[t] == 0) continue;
+    uint32_t lo = qt_lo[t], hi = qt_hi[t], q = qt_q[t];
+    uint32_t qlen = qt_len[t];
+    uint16_t qti = (uint16_t)(t - query_term_off[q]);
+    uint64_t out = qt_goff[t];
+    unsigned long long best = 0;
+    for (uint32_t base = lo; base < hi; base += 32) {
+      uint32_t term = base + lane;
+      bool live = term < hi && ix.term_df_live[term] > 0;
+      uint32_t m = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        uint64_t idx = out + __popc(m & ((1u << lane) - 1u));
+        uint64_t a = ix.term_row_begin[term], b = ix.term_row_begin[term + 1];
+        Seg s;
+        s.row_begin = a; s.n_rows = (uint32_t)(b - a); s.q = q; s.term = term; s.qlen = qlen;
+        s.qti = qti; s.mode = MODE_SECONDARY; s.pad = 0; s.slot = 0;
+        seg_g[idx] = s;
+        g_tiles[idx] = ((b + TILE_ROWS - 1) / TILE_ROWS) - (a / TILE_ROWS);
+        unsigned long long cand = ((unsigned long long)(b - a) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+        best = max(best, cand);
+      }
+      out += __popc(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, (unsigned long long)shfl_u64(best, lane ^ o));
+    if (lane == 0 && best) atomicMax(&q_prim[q], best);
+  }
+}
+
+// One thread per query: promote the elected list to PRIMARY and bound the side-path records:
+// every secondary row + at most one primary row per secondary doc.
+__global__ void gprimary_kernel(uint64_t n_queries, const unsigned long long* __restrict__ q_isg,
+                                const unsigned long long* __restrict__ q_grows,
+                                const unsigned long long* __restrict__ q_prim, Seg* __restrict__ seg_g,
+                                unsigned long long* __restrict__ q_recbound,
+                                const uint64_t* __restrict__ query_term_off,
+                                const unsigned long long* __restrict__ qt_goff,
+                                unsigned long long* __restrict__ q_gsegoff) {
+  uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (q > n_queries) return;
+  q_gsegoff[q] = qt_goff[query_term_off[q]];   // qt_goff has n_qterms + 1 entries
+  if (q == n_queries) return;
+  unsigned long long bound = 0;
+  if (q_isg[q]) {
+    unsigned long long p = q_prim[q];
+    uint32_t idx = 0xFFFFFFFFu - (uint32_t)(p & 0xFFFFFFFFull);
+    unsigned long long prows = p >> 32;
+    seg_g[idx].mode = MODE_PRIMARY;
+    bound = 2ull * (q_grows[q] - prows);
+  }
+  q_recbound[q] = bound;
+}
+
+// Assign bitmap slots for one round: slot = rank of the query among the round's class-G queries.
+__global__ void gslot_kernel(Seg* __restrict__ seg_g, uint64_t seg_begin, uint64_t seg_end,
+                             const unsigned long long* __restrict__ q_gidx, uint32_t q_begin) {
+  uint64_t i = seg_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= seg_end) return;
+  seg_g[i].slot = (uint32_t)(q_gidx[seg_g[i].q] - q_gidx[q_begin]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp iteration over a launch's virtual tile space
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t seg_of_tile(const uint64_t* __restrict__ tile_off, uint32_t sb, uint32_t se, uint64_t t) {
+  // largest s in [sb, se) with tile_off[s] <= t  (segments with zero tiles are skipped)
+  uint32_t a = sb, b = se;
+  while (a < b) {
+    uint32_t mid = (a + b) >> 1;
+    if (tile_off[mid + 1] <= t) a = mid + 1; else b = mid;
+  }
+  return a;
+}
+
+// mark (or clear) the docs of SECONDARY segments in the query's bitmap
+__global__ void __launch_bounds__(CTA_THREADS) mark_kernel(ScoreParams P, int clear) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t T = P.tile_end - P.tile_begin;
+  uint64_t t = P.tile_begin + (T * w) / W;
+  const uint64_t t1 = P.tile_begin + (T * (w + 1)) / W;
+  if (t >= t1) return;
+  uint32_t s = seg_of_tile(P.tile_off, P.seg_begin, P.seg_end, t);
+  while (t < t1) {
+    const Seg sg = P.segs[s];
+    const uint64_t st0 = P.tile_off[s], st1 = P.tile_off[s + 1];
+    const uint64_t tend = min(t1, st1);
+    if (sg.mode == MODE_SECONDARY) {
+      uint32_t* bm = P.bitmap + (size_t)sg.slot * P.bitmap_words;
+      const uint64_t abs0 = sg.row_begin / TILE_ROWS;
+      const uint64_t rend = sg.row_begin + sg.n_rows;
+      for (; t < tend; ++t) {
+        uint64_t row0 = (abs0 + (t - st0)) * TILE_ROWS + lane * 4;
+        uint4 d = ldg_stream(P.ix.post_doc + row0);
+        uint32_t dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint64_t row = row0 + j;
+          if (row >= sg.row_begin && row < rend) {
+            if (clear) bm[dv[j] >> 5] = 0u;
+            else atomicOr(&bm[dv[j] >> 5], 1u << (dv[j] & 31));
+          }
+        }
+      }
+    }
+    t = tend;
+    ++s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// THE scoring kernel.  Each warp owns a contiguous span of the launch's tile space; a tile is
+// 128 consecutive posting rows (aligned), each lane loads 4 rows of every column with one
+// 128-bit streaming load (fully coalesced 512 B per column per warp).
+// ------------------------------------------------------------------------------------------
+template <int F, int SCORER, bool GMODE>
+__global__ void __launch_bounds__(CTA_THREADS) score_kernel(const __grid_constant__ ScoreParams P) {
+  extern __shared__ double s_tab[];
+  if (SCORER == 0) {
+    for (uint32_t i = threadIdx.x; i < P.tab_total; i += blockDim.x) s_tab[i] = P.tab[i];
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t T = P.tile_end - P.tile_begin;
+  const uint64_t span0 = P.tile_begin + (T * w) / W;
+  const uint64_t span1 = P.tile_begin + (T * (w + 1)) / W;
+  if (span0 >= span1) return;
+  uint64_t t = span0;
+  uint32_t s = seg_of_tile(P.tile_off, P.seg_begin, P.seg_end, t);
+
+  WarpAcc acc;
+  acc.reset(NONE);
+  bool acc_owned = false;
+  uint64_t st_stream = 0, st_scored = 0, st_ptr = 0, st_div = 0;
+
+  while (t < span1) {
+    const Seg sg = P.segs[s];
+    const uint64_t st0 = P.tile_off[s], st1 = P.tile_off[s + 1];
+    const uint64_t tend = min(span1, st1);
+    if (tend > t) {
+      if (sg.q != acc.q) {
+        if (acc.q != NONE) acc.flush(P.out, acc_owned, lane);
+        acc.reset(sg.q);
+        // class S: the query is exactly this segment; it is "owned" when its tiles are all ours
+        acc_owned = !GMODE && st0 >= span0 && st1 <= span1;
+      }
+      // per-segment constants (before_each, bm25.rs:35-58 / zero_to_one.rs:57-58,72)
+      const uint32_t explen = P.ix.term_byte_len[sg.term];
+      double idf = 0.0, ebst = 1.0, zs = 0.0;
+      uint32_t qtl = 0;
+      if (SCORER == 0) {
+        idf = P.ix.term_idf[sg.term];
+        ebst = P.ix.eb[explen - sg.qlen];
+      } else {
+        zs = z2o_term_score(explen, sg.qlen);
+        qtl = (uint32_t)(P.query_term_off[sg.q + 1] - P.query_term_off[sg.q]);
+      }
+      const uint64_t abs0 = sg.row_begin / TILE_ROWS;
+      const uint64_t rbeg = sg.row_begin, rend = sg.row_begin + sg.n_rows;
+      const uint32_t* bm = GMODE ? (P.bitmap + (size_t)sg.slot * P.bitmap_words) : nullptr;
+
+      for (; t < tend; ++t) {
+        const uint64_t row0 = (abs0 + (t - st0)) * TILE_ROWS + lane * 4;
+        uint4 dq = ldg_stream(P.ix.post_doc + row0);
+        uint4 tq[F], lq[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          tq[f] = ldg_stream(P.ix.post_tf[f] + row0);
+          lq[f] = ldg_stream(P.ix.post_fl[f] + row0);
+        }
+        const uint32_t dv[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t row = row0 + j;
+          const uint32_t doc = dv[j];
+          bool in = row >= rbeg && row < rend;
+          bool live = in;
+          if (P.ix.has_removed && in) live = !((__ldg(&P.ix.removed[doc >> 5]) >> (doc & 31)) & 1u);
+          st_stream += in;
+          st_scored += live;
+          double score = 0.0;
+          uint32_t mult = 0;
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const uint32_t tf = (j == 0) ? tq[f].x : (j == 1) ? tq[f].y : (j == 2) ? tq[f].z : tq[f].w;
+            const uint32_t fl = (j == 0) ? lq[f].x : (j == 1) ? lq[f].y : (j == 2) ? lq[f].z : lq[f].w;
+            mult += tf;
+            if (SCORER == 0) {
+              // BM25::score, bm25.rs:60-93: score += tf' * idf * boost[x] * expansion_boost
+              double tfn;
+              if (tf < P.tab_tfcap[f] && fl < P.tab_flcap[f]) tfn = s_tab[P.tab_off[f] + tf * P.tab_flcap[f] + fl];
+              else tfn = bm25_tf_slow(P, tf, fl, f);
+              double c = __dmul_rn(__dmul_rn(__dmul_rn(tfn, idf), P.boost[f]), ebst);
+              if (tf > 0) score = __dadd_rn(score, c);
+            } else {
+              // single-event ZeroToOne: score() + finalize(), zero_to_one.rs:44-126
+              if (tf > 0) score = fmax(z2o_entry(zs, tf, fl, qtl), score);
+            }
+          }
+          if (live) st_ptr += mult;
+          bool some = live && (SCORER == 0 ? (score > 0.0) : true);
+          if (GMODE) {
+            bool divert = live && (sg.mode == MODE_SECONDARY ||
+                                   ((__ldg(&bm[doc >> 5]) >> (doc & 31)) & 1u));
+            uint32_t m = __ballot_sync(0xffffffffu, divert);
+            if (m) {
+              uint32_t base = 0;
+              if (lane == 0) base = atomicAdd(P.rec_count, (uint32_t)__popc(m));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+              if (divert) {
+                if (pos < P.rec_cap) {
+                  P.rec_key[pos] = ((unsigned long long)sg.slot << P.doc_bits) | doc;
+                  P.rec_val[pos] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)row;
+                } else {
+                  atomicOr(P.out.error_flag, 2u);
+                }
+              }
+              st_div += divert;
+            }
+            some = some && !divert;
+          }
+          acc.add(P.out, some, doc, score, lane);
+        }
+      }
+    }
+    ++s;
+  }
+  if (acc.q != NONE) acc.flush(P.out, acc_owned, lane);
+  st_stream = warp_sum_u64(st_stream); st_scored = warp_sum_u64(st_scored);
+  st_ptr = warp_sum_u64(st_ptr); st_div = warp_sum_u64(st_div);
+  if (lane == 0) {
+    atomicAdd(&P.stats[ST_ROWS_STREAMED], (unsigned long long)st_stream);
+    atomicAdd(&P.stats[ST_ROWS_SCORED], (unsigned long long)st_scored);
+    atomicAdd(&P.stats[ST_POINTER_VISITS], (unsigned long long)st_ptr);
+    atomicAdd(&P.stats[ST_ROWS_DIVERTED], (unsigned long long)st_div);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Side path: fold the events of docs that were hit by more than one (query term, expansion).
+// Records are sorted by (round slot, doc); the events of one doc are consecutive.  Within a
+// doc they must be applied in (query_term_index, expansion rank) order = ascending segment
+// index (segments are generated in that order), which is the high half of the record value.
+// ------------------------------------------------------------------------------------------
+struct FoldParams {
+  ScoreParams S;
+  const unsigned long long* key;   // sorted
+  const unsigned long long* val;
+  uint32_t n;
+};
+
+template <int F>
+__device__ __forceinline__ double bm25_row_score(const ScoreParams& P, const Seg& sg, uint32_t row) {
+  const uint32_t explen = P.ix.term_byte_len[sg.term];
+  const double idf = P.ix.term_idf[sg.term];
+  const double ebst = P.ix.eb[explen - sg.qlen];
+  double score = 0.0;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    uint32_t tf = P.ix.post_tf[f][row], fl = P.ix.post_fl[f][row];
+    if (tf > 0) {
+      double tfn = (tf < P.tab_tfcap[f] && fl < P.tab_flcap[f]) ? P.tab[P.tab_off[f] + tf * P.tab_flcap[f] + fl]
+                                                                 : bm25_tf_slow(P, tf, fl, f);
+      double c = __dmul_rn(__dmul_rn(__dmul_rn(tfn, idf), P.boost[f]), ebst);
+      score = __dadd_rn(score, c);
+    }
+  }
+  return score;
+}
+
+// next event of the doc in ascending value order: smallest val > last (vals are distinct)
+__device__ __forceinline__ bool next_event(const unsigned long long* val, uint32_t a, uint32_t b, bool first,
+                                           unsigned long long last, unsigned long long* out) {
+  bool found = false;
+  unsigned long long best = 0;
+  for (uint32_t j = a; j < b; ++j) {
+    unsigned long long v = val[j];
+    if ((first || v > last) && (!found || v < best)) { best = v; found = true; }
+  }
+  *out = best;
+  return found;
+}
+
+template <int F, int SCORER>
+__global__ void __launch_bounds__(CTA_THREADS) fold_kernel(const __grid_constant__ FoldParams FP) {
+  const ScoreParams& P = FP.S;
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t n32 = (FP.n + 31) / 32;
+  const uint64_t g0 = (n32 * w) / W, g1 = (n32 * (w + 1)) / W;
+  WarpAcc acc;
+  acc.reset(NONE);
+  for (uint64_t g = g0; g < g1; ++g) {
+    const uint32_t i = (uint32_t)(g * 32 + lane);
+    bool head = false;
+    unsigned long long key = 0;
+    if (i < FP.n) {
+      key = FP.key[i];
+      head = (i == 0) || (FP.key[i - 1] != key);
+    }
+    bool has = false;
+    double result = 0.0;
+    uint32_t doc = 0, q = NONE;
+    if (head) {
+      uint32_t e = i + 1;
+      while (e < FP.n && FP.key[e] == key) ++e;
+      doc = (uint32_t)(key & ((1ull << P.doc_bits) - 1ull));
+      q = P.segs[(uint32_t)(FP.val[i] >> 32)].q;
+      if (SCORER == 0) {
+        // max_score_merger, query.rs:150-164, as the per-doc fold of SURVEY Appendix B
+        uint32_t cur = NONE;
+        unsigned long long last = 0, v;
+        bool first_ev = true;
+        while (next_event(FP.val, i, e, first_ev, last, &v)) {
+          first_ev = false; last = v;
+          const Seg sg = P.segs[(uint32_t)(v >> 32)];
+          bool firstq = (sg.qti != cur);
+          cur = sg.qti;
+          double sc = bm25_row_score<F>(P, sg, (uint32_t)v);
+          if (!(sc > 0.0)) continue;                 // None: the doc is still marked visited
+          if (!has) { result = sc; has = true; }
+          else if (firstq) result = __dadd_rn(result, sc);
+          else result = fmax(result, sc);
+        }
+      } else {
+        // ZeroToOne::finalize, zero_to_one.rs:84-126.  Entries of field x = events with
+        // tf[x] > 0, visited by (score desc, event order asc) = a stable sort by score;
+        // accept iff the query term is not consumed and the term's pool is not exhausted
+        // (accepted so far with this term < tf[x]).
+        has = true;
+        const uint32_t qtl = (uint32_t)(P.query_term_off[q + 1] - P.query_term_off[q]);
+        const uint32_t ne = e - i;
+#pragma unroll 1
+        for (int x = 0; x < F; ++x) {
+          double accx = 0.0;
+          // "processed" / "accepted" flags per event: bit masks over the (unsorted) positions
+          unsigned long long done_lo = 0, acc_lo = 0;
+          for (uint32_t step = 0; step < ne; ++step) {
+            // pick the unprocessed entry with max score, ties by smaller val
+            int bj = -1; double bs = 0.0; unsigned long long bv = 0; uint32_t btf = 0, bfl = 0, bterm = 0, bqti = 0;
+            for (uint32_t j = 0; j < ne && j < 64; ++j) {
+              if ((done_lo >> j) & 1ull) continue;
+              unsigned long long v = FP.val[i + j];
+              uint32_t row = (uint32_t)v;
+              uint32_t tf = P.ix.post_tf[x][row];
+              if (tf == 0) { done_lo |= 1ull << j; continue; }
+              const Seg sg = P.segs[(uint32_t)(v >> 32)];
+              double sc = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
+              if (bj < 0 || sc > bs || (sc == bs && v < bv)) {
+                bj = (int)j; bs = sc; bv = v; btf = tf; bfl = P.ix.post_fl[x][row]; bterm = sg.term; bqti = sg.qti;
+              }
+            }
+            if (bj < 0) break;
+            done_lo |= 1ull << bj;
+            bool consumed = false; uint32_t used = 0;
+            for (uint32_t j = 0; j < ne && j < 64; ++j) {
+              if (!((acc_lo >> j) & 1ull)) continue;
+              const Seg sg = P.segs[(uint32_t)(FP.val[i + j] >> 32)];
+              consumed |= (sg.qti == bqti);
+              used += (sg.term == bterm);
+            }
+            if (consumed || used >= btf) continue;
+            acc_lo |= 1ull << bj;
+            accx = __dadd_rn(accx, z2o_entry(bs, btf, bfl, qtl));
+          }
+          result = fmax(accx, result);
+        }
+        if (ne > 64) atomicOr(P.out.error_flag, 4u);   // > 64 events on one doc: outside the envelope
+      }
+    }
+    // emit: lanes may belong to different queries (sorted, so at most a few switches)
+    uint32_t m = __ballot_sync(0xffffffffu, has);
+    while (m) {
+      int l = __ffs(m) - 1;
+      uint32_t ql = __shfl_sync(0xffffffffu, q, l);
+      bool mine = has && q == ql;
+      if (acc.q != ql) {
+        if (acc.q != NONE) acc.flush(P.out, false, lane);
+        acc.reset(ql);
+      }
+      acc.add(P.out, mine, doc, result, lane);
+      m &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  }
+  if (acc.q != NONE) acc.flush(P.out, false, lane);
+}
+
+// One warp per query: merge the partial top-k lists into the final (score desc, doc asc) top-k.
+__global__ void __launch_bounds__(CTA_THREADS) finalize_kernel(Outputs o, uint64_t n_queries) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  if (o.k == 0) return;
+  for (uint64_t q = w; q < n_queries; q += W) {
+    uint32_t p = o.part_head[q];
+    if (p == NONE) continue;
+    WarpAcc acc;
+    acc.reset((uint32_t)q);
+    while (p != NONE) {
+      uint32_t n = o.part_n[p];
+      bool v = lane < (int)n;
+      uint32_t d = v ? o.part_doc[(size_t)p * o.k + lane] : NONE;
+      double s = v ? o.part_score[(size_t)p * o.k + lane] : -1.0;
+      acc.insert_candidates(v && better(s, d, acc.thr_s, acc.thr_d), d, s, lane, (int)o.k);
+      p = o.part_next[p];
+    }
+    uint32_t ntop = (uint32_t)min((unsigned long long)o.k, o.n_results[q]);
+    if (lane < (int)ntop) {
+      o.topk_doc[(size_t)q * o.k + lane] = acc.td;
+      o.topk_score[(size_t)q * o.k + lane] = acc.ts;
+    }
+    if (lane == 0) o.topk_n[q] = ntop;
+  }
+}
+
+}  // namespace pbk

@@ -1,0 +1,340 @@
+"""Host-side mirror of the reference's public surface for the query path.
+
+`Index` keeps the names, argument meaning and error behaviour of `probly_search::Index`
+(src/index.rs:35-199, src/query.rs:17-106): `Index(fields_num)`, `add_document(field_accessors,
+tokenizer, key, doc)`, `remove_document(key)`, `vacuum()`, `query(query, score_calculator,
+tokenizer, fields_boost) -> [QueryResult]`, plus the batch entry `query_batch`.  All work goes
+through the C ABI (include/probly_b200.h); there is no Python implementation of the path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Callable, Hashable, List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .score import scorer_params
+
+
+@dataclass(frozen=True)
+class QueryResult:
+    """src/query.rs:9-15"""
+    key: Any
+    score: float
+
+
+Tokenizer = Callable[[str], List[str]]          # src/lib.rs:14
+FieldAccessor = Callable[[Any], List[str]]      # src/lib.rs:11
+
+
+def _flat_tokens(tokens: Sequence[str]):
+    enc = [t.encode("utf-8") for t in tokens]
+    off = np.zeros(len(enc) + 1, dtype=np.uint64)
+    if enc:
+        off[1:] = np.cumsum([len(e) for e in enc], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+    return buf, off
+
+
+class FlatQueries:
+    """A query batch in the layout of `pb_query_batch_desc`: every query already tokenized."""
+
+    def __init__(self, query_term_off: np.ndarray, term_byte_off: np.ndarray, term_bytes: np.ndarray):
+        self.query_term_off = np.ascontiguousarray(query_term_off, dtype=np.uint64)
+        self.term_byte_off = np.ascontiguousarray(term_byte_off, dtype=np.uint64)
+        self.term_bytes = np.ascontiguousarray(term_bytes, dtype=np.uint8)
+
+    @property
+    def n_queries(self) -> int:
+        return len(self.query_term_off) - 1
+
+    @classmethod
+    def from_strings(cls, queries: Sequence[str], tokenizer: Tokenizer) -> "FlatQueries":
+        toks: List[str] = []
+        qoff = [0]
+        for q in queries:
+            toks.extend(tokenizer(q))
+            qoff.append(len(toks))
+        buf, off = _flat_tokens(toks)
+        return cls(np.asarray(qoff, dtype=np.uint64), off, buf)
+
+    def slice(self, lo: int, hi: int) -> "FlatQueries":
+        t0, t1 = int(self.query_term_off[lo]), int(self.query_term_off[hi])
+        b0, b1 = int(self.term_byte_off[t0]), int(self.term_byte_off[t1])
+        return FlatQueries(self.query_term_off[lo:hi + 1] - np.uint64(t0),
+                           self.term_byte_off[t0:t1 + 1] - np.uint64(b0),
+                           np.concatenate([self.term_bytes[b0:b1], np.zeros(1, np.uint8)]))
+
+    def terms_of(self, q: int) -> List[str]:
+        out = []
+        for t in range(int(self.query_term_off[q]), int(self.query_term_off[q + 1])):
+            out.append(bytes(self.term_bytes[int(self.term_byte_off[t]):int(self.term_byte_off[t + 1])]).decode())
+        return out
+
+
+class BatchResults:
+    """Per-query outputs of `pb_query_batch` (include/probly_b200.h `pb_query_results`)."""
+
+    def __init__(self, n: int, k: int):
+        kk = max(k, 1)
+        self.k = k
+        self.n_results = np.zeros(n, dtype=np.uint64)
+        self.doc_digest = np.zeros(n, dtype=np.uint64)
+        self.score_digest = np.zeros(n, dtype=np.uint64)
+        self.topk_n = np.zeros(n, dtype=np.uint32)
+        self.topk_doc = np.zeros((n, kk), dtype=np.uint32)
+        self.topk_score = np.zeros((n, kk), dtype=np.float64)
+
+    def c_struct(self) -> capi.QueryResults:
+        return capi.QueryResults(self.n_results.ctypes.data, self.doc_digest.ctypes.data,
+                                 self.score_digest.ctypes.data, self.topk_n.ctypes.data,
+                                 self.topk_doc.ctypes.data, self.topk_score.ctypes.data)
+
+
+class Index:
+    """Mirror of `Index<T>` (src/index.rs:19-33).  Keys may be any hashable; the device works on
+    dense ordinals and the host keeps ordinal -> key."""
+
+    def __init__(self, fields_num: int, device: int = 0):
+        self._L = capi.lib()
+        self.fields_num = fields_num
+        self.device = device
+        h = C.c_void_p()
+        capi.check(self._L.pb_builder_create(fields_num, C.byref(h)))
+        self._b = h
+        self._ix: Optional[C.c_void_p] = None
+        self._image_dirty = True        # structure changed: re-flatten + upload
+        self._live_dirty = False        # only the removed set / stats changed
+        self._key_to_id: dict = {}
+        self._id_to_key: list = []
+        self._ord_to_id: Optional[np.ndarray] = None
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ix", None):
+            self._L.pb_index_destroy(self._ix)
+            self._ix = None
+        if getattr(self, "_b", None):
+            self._L.pb_builder_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- mutation (src/index.rs:77-199) --------------------------------------------------------
+    def _key_id(self, key: Hashable) -> int:
+        i = self._key_to_id.get(key)
+        if i is None:
+            i = len(self._id_to_key)
+            self._key_to_id[key] = i
+            self._id_to_key.append(key)
+        return i
+
+    def add_document(self, field_accessors: Sequence[FieldAccessor], tokenizer: Tokenizer, key: Hashable,
+                     doc: Any) -> None:
+        """src/index.rs:77-158"""
+        toks: List[str] = []
+        vcount: List[int] = []
+        fcount: List[int] = []
+        for i in range(self.fields_num):
+            values = field_accessors[i](doc)
+            fcount.append(len(values))
+            for v in values:
+                t = tokenizer(v)
+                vcount.append(len(t))
+                toks.extend(t)
+        buf, off = _flat_tokens(toks)
+        vc = np.asarray(vcount + [0], dtype=np.uint32)
+        fc = np.asarray(fcount, dtype=np.uint32)
+        d = capi.DocTokens(buf.ctypes.data, off.ctypes.data, vc.ctypes.data, fc.ctypes.data)
+        capi.check(self._L.pb_builder_add_document(self._b, self._key_id(key), C.byref(d)))
+        self._image_dirty = True
+
+    def add_documents_flat(self, keys: np.ndarray, tok_bytes: np.ndarray, tok_off: np.ndarray,
+                           field_tok_count: np.ndarray) -> None:
+        """Bulk add with integer keys (pb_builder_add_documents): one value per field."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        if self._id_to_key:
+            raise ValueError("add_documents_flat cannot be mixed with add_document on one index")
+        self._flat_keys = True
+        capi.check(self._L.pb_builder_add_documents(self._b, len(keys), keys.ctypes.data, tok_bytes.ctypes.data,
+                                                    tok_off.ctypes.data, field_tok_count.ctypes.data))
+        self._image_dirty = True
+
+    def remove_document(self, key: Hashable) -> None:
+        """src/index.rs:161-191 — lazy: the postings stay until vacuum()."""
+        kid = key if getattr(self, "_flat_keys", False) else self._key_to_id.get(key)
+        if kid is None:
+            return
+        capi.check(self._L.pb_builder_remove_document(self._b, int(kid)))
+        self._live_dirty = True
+
+    def vacuum(self) -> None:
+        """src/index.rs:194-199"""
+        capi.check(self._L.pb_builder_vacuum(self._b))
+        self._image_dirty = True
+
+    def info(self) -> capi.BuilderInfo:
+        out = capi.BuilderInfo()
+        capi.check(self._L.pb_builder_get_info(self._b, C.byref(out)))
+        return out
+
+    def flatten(self) -> capi.IndexImage:
+        im = capi.IndexImage()
+        capi.check(self._L.pb_builder_flatten(self._b, C.byref(im)))
+        return im
+
+    # -- device image --------------------------------------------------------------------------
+    def sync_device(self) -> None:
+        """Brings the HBM image up to date with the host index (flatten + upload, or just the
+        removed mask / N / avg when only remove_document happened)."""
+        if self._ix is not None and not self._image_dirty and not self._live_dirty:
+            return
+        im = self.flatten()
+        if self._ix is None or self._image_dirty:
+            if self._ix is not None:
+                self._L.pb_index_destroy(self._ix)
+                self._ix = None
+            h = C.c_void_p()
+            capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
+            self._ix = h
+        else:
+            nd = int(im.n_docs)
+            words = np.ctypeslib.as_array(im.removed_bitmap, shape=((nd + 31) // 32 + 1,))
+            bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:nd]
+            ords = np.ascontiguousarray(np.nonzero(bits)[0], dtype=np.uint32)
+            avg = (C.c_double * 4)(*[im.field_avg[i] for i in range(4)])
+            capi.check(self._L.pb_index_set_live_state(self._ix, ords.ctypes.data, len(ords), im.n_live_docs, avg))
+        nd = int(im.n_docs)
+        self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
+        self._image_dirty = False
+        self._live_dirty = False
+
+    def _key_of_ord(self, o: int):
+        kid = int(self._ord_to_id[o])
+        return kid if getattr(self, "_flat_keys", False) else self._id_to_key[kid]
+
+    def _desc(self, fq: FlatQueries, score_calculator, fields_boost: Sequence[float], top_k: int):
+        scorer, k1, b = scorer_params(score_calculator)
+        boosts = np.asarray(list(fields_boost), dtype=np.float64)
+        d = capi.QueryBatchDesc(fq.n_queries, fq.query_term_off.ctypes.data, fq.term_byte_off.ctypes.data,
+                                fq.term_bytes.ctypes.data, scorer, k1, b, boosts.ctypes.data, len(boosts), top_k)
+        return d, boosts
+
+    # -- queries -------------------------------------------------------------------------------
+    def expand_term(self, term: str) -> List[str]:
+        """src/query.rs:109-126 (private there; exposed for the expansion-order goldens)."""
+        self.sync_device()
+        tb = np.frombuffer(term.encode("utf-8") + b"\0", dtype=np.uint8)
+        n, need = C.c_uint64(0), C.c_uint64(0)
+        capi.check(self._L.pb_index_expand_term(self._ix, tb.ctypes.data, len(tb) - 1, None, 0, C.byref(n), C.byref(need)))
+        if n.value == 0:
+            return []
+        out = np.zeros(need.value + 1, dtype=np.uint8)
+        capi.check(self._L.pb_index_expand_term(self._ix, tb.ctypes.data, len(tb) - 1, out.ctypes.data, need.value,
+                                                C.byref(n), C.byref(need)))
+        return bytes(out[: need.value]).decode("utf-8").split("\n")
+
+    def query_full_flat(self, fq: FlatQueries, score_calculator, fields_boost: Sequence[float],
+                        cap: Optional[int] = None):
+        """Full result sets of every query of the batch: arrays (query, doc ordinal, score), unordered."""
+        self.sync_device()
+        d, _keep = self._desc(fq, score_calculator, fields_boost, 0)
+        cap = int(cap if cap is not None else max(1024, fq.n_queries * 64))
+        while True:
+            oq = np.zeros(cap, dtype=np.uint32)
+            od = np.zeros(cap, dtype=np.uint32)
+            os_ = np.zeros(cap, dtype=np.float64)
+            n = C.c_uint64(0)
+            rc = self._L.pb_query_full(self._ix, C.byref(d), cap, oq.ctypes.data, od.ctypes.data, os_.ctypes.data, C.byref(n))
+            if rc == capi.PB_ERR_CAPACITY:
+                cap = int(n.value) + 16
+                continue
+            capi.check(rc)
+            return oq[: n.value], od[: n.value], os_[: n.value]
+
+    def query(self, query: str, score_calculator, tokenizer: Tokenizer, fields_boost: Sequence[float]) -> List[QueryResult]:
+        """src/query.rs:21-106.  Result order: score descending; exactly tied scores by document
+        ordinal ascending (the reference leaves ties in hash order, SURVEY §3.4 rule 10)."""
+        fq = FlatQueries.from_strings([query], tokenizer)
+        _, docs, scores = self.query_full_flat(fq, score_calculator, fields_boost)
+        order = np.lexsort((docs, -scores))
+        return [QueryResult(self._key_of_ord(int(docs[i])), float(scores[i])) for i in order]
+
+    def query_batch_flat(self, fq: FlatQueries, score_calculator, fields_boost: Sequence[float], top_k: int = 10) -> BatchResults:
+        """pb_query_batch: host buffers in, host buffers out."""
+        self.sync_device()
+        d, _keep = self._desc(fq, score_calculator, fields_boost, top_k)
+        res = BatchResults(fq.n_queries, top_k)
+        rs = res.c_struct()
+        capi.check(self._L.pb_query_batch(self._ix, C.byref(d), C.byref(rs)))
+        return res
+
+    def query_batch(self, queries: Sequence[str], score_calculator, tokenizer: Tokenizer,
+                    fields_boost: Sequence[float], top_k: int = 10) -> List[List[QueryResult]]:
+        """Batch form of `query`: the top_k best results of every query."""
+        fq = FlatQueries.from_strings(queries, tokenizer)
+        r = self.query_batch_flat(fq, score_calculator, fields_boost, top_k)
+        out = []
+        for q in range(fq.n_queries):
+            n = int(r.topk_n[q])
+            out.append([QueryResult(self._key_of_ord(int(r.topk_doc[q, i])), float(r.topk_score[q, i])) for i in range(n)])
+        return out
+
+    def last_stats(self) -> dict:
+        s = capi.BatchStats()
+        capi.check(self._L.pb_index_last_stats(self._ix, C.byref(s)))
+        return s.as_dict()
+
+    def term_df_live(self) -> np.ndarray:
+        self.sync_device()
+        im = self.flatten()
+        out = np.zeros(max(int(im.n_terms), 1), dtype=np.uint64)
+        capi.check(self._L.pb_index_term_df_live(self._ix, out.ctypes.data, len(out)))
+        return out[: int(im.n_terms)]
+
+
+class DeviceBatch:
+    """Staged form of a batch (pb_batch_create / run / fetch): upload once, run many times with
+    the inputs resident in HBM."""
+
+    def __init__(self, index: Index, fq: FlatQueries, score_calculator, fields_boost: Sequence[float], top_k: int = 10):
+        index.sync_device()
+        self._L = index._L
+        self.index = index
+        self.fq = fq
+        self.top_k = top_k
+        d, self._boosts = index._desc(fq, score_calculator, fields_boost, top_k)
+        h = C.c_void_p()
+        capi.check(self._L.pb_batch_create(index._ix, C.byref(d), C.byref(h)))
+        self._h = h
+
+    def run(self) -> None:
+        capi.check(self._L.pb_batch_run(self._h))
+
+    def fetch(self) -> BatchResults:
+        res = BatchResults(self.fq.n_queries, self.top_k)
+        rs = res.c_struct()
+        capi.check(self._L.pb_batch_fetch(self._h, C.byref(rs)))
+        return res
+
+    def stats(self) -> dict:
+        s = capi.BatchStats()
+        capi.check(self._L.pb_batch_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.pb_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
