@@ -170,9 +170,10 @@ typedef struct pb_query_batch_desc {
 
 /* Per-query outputs.  Any pointer may be NULL (that output is skipped).
  * Digests (order independent, wrap-around sums over the result set):
- *   h(d)        = x=(d+1)*0x9E3779B97F4A7C15; x^=x>>32; x*=0xD6E8FEB86659FD93; x^=x>>32
- *   doc_digest  = sum h(doc ordinal)
- *   score_digest= sum g(d,s), g = y=(h(d)^bits(s))*0xD6E8FEB86659FD93; y^=y>>32
+ *   a(d)        = x = (u32)(d+1) * 0x9E3779B1; x ^= x >> 16                       (32-bit)
+ *   doc_digest  = sum (u64)a(d) * 0xD6E8FEB9
+ *   score_digest= sum (u64)y * 0xC2B2AE3D,  y = lo(s) ^ hi(s)*0x85EBCA77 ^ a(d); y ^= y >> 15
+ *                 (lo/hi = the two 32-bit halves of the f64 score's bit pattern)
  * top-k rows are ordered (score desc, doc ordinal asc) — the reference's comparison rule
  * (src/lib.rs:54-58) when ordinals follow key order. */
 typedef struct pb_query_results {
@@ -192,6 +193,10 @@ int pb_batch_create(pb_index* ix, const pb_query_batch_desc* q, pb_batch** out);
 int pb_batch_run(pb_batch* b);
 int pb_batch_fetch(pb_batch* b, pb_query_results* out);
 void pb_batch_destroy(pb_batch* b);
+/* DEVICE pointers of the batch's result buffers (same layout as pb_query_results), valid until
+ * the batch is re-run or destroyed: lets a caller hand the top-k block straight to NCCL for the
+ * multi-GPU gather without a host round trip. */
+int pb_batch_device_results(pb_batch* b, pb_query_results* out_device_ptrs);
 
 typedef struct pb_batch_stats {
   uint64_t n_queries, n_query_terms;

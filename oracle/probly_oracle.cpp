@@ -647,16 +647,17 @@ struct ZeroToOne {
 
 // Order-independent digests shared (by definition, not by code) with the GPU
 // path: see include/probly_b200.h "Digests".
-static inline uint64_t doc_hash(uint64_t doc) {
-  uint64_t x = (doc + 1) * 0x9E3779B97F4A7C15ULL;
-  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 32;
-  return x;
+static inline uint32_t doc_mix(uint64_t doc) {
+  uint32_t a = ((uint32_t)doc + 1u) * 0x9E3779B1u;
+  return a ^ (a >> 16);
 }
+static inline uint64_t doc_hash(uint64_t doc) { return (uint64_t)doc_mix(doc) * 0xD6E8FEB9u; }
 static inline uint64_t score_hash(uint64_t doc, double score) {
   uint64_t b; std::memcpy(&b, &score, 8);
-  uint64_t x = (doc_hash(doc) ^ b) * 0xD6E8FEB86659FD93ULL;
-  x ^= x >> 32;
-  return x;
+  uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+  uint32_t y = lo ^ (hi * 0x85EBCA77u) ^ doc_mix(doc);
+  y ^= y >> 15;
+  return (uint64_t)y * 0xC2B2AE3Du;
 }
 
 }  // namespace orc

@@ -85,7 +85,7 @@ EXPORTS = [
     "pb_builder_remove_document", "pb_builder_vacuum", "pb_builder_get_info", "pb_builder_flatten",
     "pb_device_count", "pb_index_create", "pb_index_set_live_state", "pb_index_destroy",
     "pb_index_expand_term", "pb_index_term_df_live", "pb_query_batch", "pb_batch_create", "pb_batch_run",
-    "pb_batch_fetch", "pb_batch_destroy", "pb_batch_get_stats", "pb_index_last_stats", "pb_query_full",
+    "pb_batch_fetch", "pb_batch_destroy", "pb_batch_device_results", "pb_batch_get_stats", "pb_index_last_stats", "pb_query_full",
     "pb_host_alloc", "pb_host_free", "pb_last_error", "pb_version",
 ]
 
@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
         "pb_batch_run": (i32, [vp]),
         "pb_batch_fetch": (i32, [vp, P(QueryResults)]),
         "pb_batch_destroy": (None, [vp]),
+        "pb_batch_device_results": (i32, [vp, P(QueryResults)]),
         "pb_batch_get_stats": (i32, [vp, P(BatchStats)]),
         "pb_index_last_stats": (i32, [vp, P(BatchStats)]),
         "pb_query_full": (i32, [vp, P(QueryBatchDesc), u64, vp, vp, vp, P(u64)]),

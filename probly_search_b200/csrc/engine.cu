@@ -94,7 +94,7 @@ struct pb_index {
   uint32_t max_term_bytes = 0, max_tf[4] = {0, 0, 0, 0}, max_fl[4] = {0, 0, 0, 0};
   DBuf<uint32_t> node_edge_begin, node_term_lo, node_term_hi, edge_char, edge_child;
   DBuf<uint64_t> term_row_begin;
-  DBuf<uint32_t> term_byte_len, post_doc, post_tf[4], post_fl[4], removed, live_prefix;
+  DBuf<uint32_t> term_byte_len, post_doc, post_tf[4], post_fl[4], removed, live_prefix, term_live_rows;
   DBuf<uint64_t> term_df_live, liverows_prefix;
   DBuf<double> term_idf, eb;
   // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
@@ -113,7 +113,7 @@ struct pb_index {
     v.post_doc = post_doc.p;
     for (int f = 0; f < 4; ++f) { v.post_tf[f] = post_tf[f].p; v.post_fl[f] = post_fl[f].p; }
     v.removed = removed.p;
-    v.term_df_live = term_df_live.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
+    v.term_df_live = term_df_live.p; v.term_live_rows = term_live_rows.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
     v.term_idf = term_idf.p; v.eb = eb.p;
     v.n_terms = (uint32_t)n_terms; v.n_docs = (uint32_t)n_docs; v.num_fields = F;
     v.has_removed = n_removed ? 1u : 0u;
@@ -132,6 +132,8 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
   for (uint32_t f = 0; f < ix->F; ++f) ix->avg[f] = avg[f];
   const size_t NT = ix->n_terms;
   CU(ix->term_df_live.ensure(NT + 1));
+  CU(ix->term_live_rows.ensure(NT + 1));
+  CU(cudaMemset(ix->term_live_rows.p, 0, (NT + 1) * sizeof(uint32_t)));
   CU(ix->live_prefix.ensure(NT + 2));
   CU(ix->liverows_prefix.ensure(NT + 2));
   CU(ix->term_idf.ensure(NT + 1));
@@ -140,10 +142,10 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
     IndexView v = ix->view();
     int grid = ix->sm_count * 8;
     switch (ix->F) {
-      case 1: live_df_kernel<1><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
-      case 2: live_df_kernel<2><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
-      case 3: live_df_kernel<3><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
-      default: live_df_kernel<4><<<grid, 256>>>(v, (ull*)ix->term_df_live.p); break;
+      case 1: live_df_kernel<1><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
+      case 2: live_df_kernel<2><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
+      case 3: live_df_kernel<3><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
+      default: live_df_kernel<4><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
     }
     CU(cudaGetLastError());
   }
@@ -208,6 +210,7 @@ struct pb_batch {
   // BM25 table
   DBuf<double> tab;
   uint32_t tab_tfcap[4] = {}, tab_flcap[4] = {}, tab_off[4] = {}, tab_total = 0;
+  bool tab_full = false;
   // host staging
   std::vector<ull> h_recoff, h_gidx, h_gsegoff, h_gtileoff;
   pb_batch_stats st{};
@@ -267,6 +270,8 @@ int batch_build_table(pb_batch* b) {
     off += tfc[f] * flc[f];
   }
   b->tab_total = off;
+  b->tab_full = true;
+  for (uint32_t f = 0; f < ix->F; ++f) if (tfc[f] <= ix->max_tf[f] || flc[f] <= ix->max_fl[f]) b->tab_full = false;
   CU(b->tab.ensure(off + 1));
   CU(cudaMemcpyAsync(b->tab.p, h.data(), off * sizeof(double), cudaMemcpyHostToDevice, b->stream));
   CU(cudaStreamSynchronize(b->stream));   // h goes out of scope
@@ -443,7 +448,7 @@ int batch_run(pb_batch* b) {
   // ---- plan ------------------------------------------------------------------------------
   plan_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(view, Q, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p,
                                                                  b->qt_len.p, b->seg_s.p, b->s_tiles.p, b->qt_gcount.p,
-                                                                 b->qt_q.p, b->q_isg.p, b->q_grows.p);
+                                                                 b->qt_q.p, b->q_isg.p, b->q_grows.p, b->stats.p);
   CU(cudaGetLastError());
   ++launches;
   RC(scan_ull(b, b->s_tiles.p, b->s_tile_off.p, Q + 1));
@@ -468,7 +473,7 @@ int batch_run(pb_batch* b) {
     CU(b->g_tile_off.ensure(n_gsegs + 2));
     gfill_kernel<<<ix->sm_count * 8, 256, 0, st>>>(view, NT, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p, b->qt_len.p,
                                                    b->qt_q.p, b->qt_gcount.p, b->qt_goff.p, b->seg_g.p, b->g_tiles.p,
-                                                   b->q_prim.p);
+                                                   b->q_prim.p, b->stats.p + ST_COUNT);
     CU(cudaGetLastError());
     gprimary_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q, b->q_isg.p, b->q_grows.p, b->q_prim.p, b->seg_g.p,
                                                                      b->q_recbound.p, b->query_term_off.p, b->qt_goff.p,
@@ -530,6 +535,9 @@ int batch_run(pb_batch* b) {
   P.k1 = b->k1; P.b = b->b; P.one_minus_b = 1.0 - b->b; P.k1_plus_1 = b->k1 + 1.0;
   for (int f = 0; f < 4; ++f) { P.boost[f] = b->boost[f]; P.avg[f] = ix->avg[f]; P.tab_tfcap[f] = b->tab_tfcap[f]; P.tab_flcap[f] = b->tab_flcap[f]; P.tab_off[f] = b->tab_off[f]; }
   P.tab = b->tab.p; P.tab_total = b->scorer == 0 ? b->tab_total : 0;
+  P.tab_full = b->tab_full ? 1u : 0u;
+  P.boosts_all_one = 1u;
+  for (uint32_t f = 0; f < ix->F; ++f) if (b->boost[f] != 1.0) P.boosts_all_one = 0u;
   P.doc_bits = doc_bits; P.bitmap_words = bitmap_words;
   P.rec_count = b->counters.p + 1;
   CU(cudaEventRecord(b->ev[2], st));
@@ -829,6 +837,15 @@ int pb_batch_fetch(pb_batch* b, pb_query_results* out) {
 }
 
 void pb_batch_destroy(pb_batch* b) { delete b; }
+
+int pb_batch_device_results(pb_batch* b, pb_query_results* o) {
+  if (!b || !o) return PB_ERR_INVALID;
+  if (!b->ran) { pb::set_error("pb_batch_device_results: batch has not been run"); return PB_ERR_INVALID; }
+  o->n_results = (uint64_t*)b->n_results.p; o->doc_digest = (uint64_t*)b->doc_digest.p;
+  o->score_digest = (uint64_t*)b->score_digest.p; o->topk_n = b->topk_n.p; o->topk_doc = b->topk_doc.p;
+  o->topk_score = b->topk_score.p;
+  return PB_OK;
+}
 
 int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out) {
   if (!b || !out) return PB_ERR_INVALID;

@@ -58,6 +58,7 @@ struct IndexView {
   const uint32_t* post_fl[4];
   const uint32_t* removed;        // bitmap, bit set = doc not live
   const uint64_t* term_df_live;
+  const uint32_t* term_live_rows; // rows of the term whose doc is live
   const uint32_t* live_prefix;    // [n_terms+1] number of terms with df_live > 0 before t
   const uint64_t* liverows_prefix;// [n_terms+1] rows of live terms before t
   const double* term_idf;         // bm25.rs:56, host libm
@@ -110,6 +111,8 @@ struct ScoreParams {
   double avg[4];
   const double* tab;             // [F][tfcap][flcap] saturated tf (bm25.rs:78-82), host-computed
   uint32_t tab_tfcap[4], tab_flcap[4], tab_off[4], tab_total;
+  uint32_t tab_full;             // the table covers every (tf, fl) present in the index
+  uint32_t boosts_all_one;       // every fields_boost is exactly 1.0
   // side path
   uint32_t* bitmap;              // [slots][bitmap_words]
   uint32_t bitmap_words;
@@ -132,15 +135,18 @@ __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
   return r;
 }
 
-__device__ __forceinline__ uint64_t doc_hash(uint32_t doc) {
-  uint64_t x = (uint64_t(doc) + 1ull) * 0x9E3779B97F4A7C15ull;
-  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
-  return x;
+// Digest hashes (include/probly_b200.h "Digests"): cheap on purpose, they run once per result.
+__device__ __forceinline__ uint32_t doc_mix(uint32_t doc) {
+  uint32_t a = (doc + 1u) * 0x9E3779B1u;
+  return a ^ (a >> 16);
 }
-__device__ __forceinline__ uint64_t score_hash(uint64_t dh, double s) {
-  uint64_t y = (dh ^ (uint64_t)__double_as_longlong(s)) * 0xD6E8FEB86659FD93ull;
-  y ^= y >> 32;
-  return y;
+__device__ __forceinline__ uint64_t doc_hash_from_mix(uint32_t a) { return (uint64_t)a * 0xD6E8FEB9u; }
+__device__ __forceinline__ uint64_t doc_hash(uint32_t doc) { return doc_hash_from_mix(doc_mix(doc)); }
+__device__ __forceinline__ uint64_t score_hash_from_mix(uint32_t a, double s) {
+  uint32_t lo = (uint32_t)__double2loint(s), hi = (uint32_t)__double2hiint(s);
+  uint32_t y = lo ^ (hi * 0x85EBCA77u) ^ a;
+  y ^= y >> 15;
+  return (uint64_t)y * 0xC2B2AE3Du;
 }
 
 __device__ __forceinline__ bool better(double as, uint32_t ad, double bs, uint32_t bd) {
@@ -221,21 +227,50 @@ struct WarpAcc {
   __device__ __forceinline__ void add(const Outputs& o, bool valid, uint32_t doc, double s, int lane) {
     if (valid) {
       ++cnt;
-      uint64_t h = doc_hash(doc);
-      dd += h;
-      sd += score_hash(h, s);
+      uint32_t a = doc_mix(doc);
+      dd += doc_hash_from_mix(a);
+      sd += score_hash_from_mix(a, s);
     }
-    if (o.full_q) {
-      uint32_t m = __ballot_sync(0xffffffffu, valid);
-      if (m) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(o.full_count, (unsigned long long)__popc(m));
-        base = shfl_u64(base, 0);
-        unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-        if (valid && pos < o.full_cap) { o.full_q[pos] = q; o.full_doc[pos] = doc; o.full_score[pos] = s; }
+    if (o.full_q) capture(o, valid, doc, s, lane);
+    if (o.k) insert_candidates(valid && better(s, doc, thr_s, thr_d), doc, s, lane, (int)o.k);
+  }
+
+  // Four rows per lane at once (the scoring kernel's tile shape).  `some` = 4-bit mask of rows
+  // that produced a result.  The top-k structure is only touched when some lane holds a score
+  // that reaches the current k-th best.
+  __device__ __forceinline__ void add4(const Outputs& o, uint32_t some, const uint32_t (&doc)[4],
+                                       const double (&sc)[4], int lane) {
+    cnt += __popc(some);
+    double best = -2.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((some >> j) & 1u) {
+        uint32_t a = doc_mix(doc[j]);
+        dd += doc_hash_from_mix(a);
+        sd += score_hash_from_mix(a, sc[j]);
+        best = fmax(best, sc[j]);
       }
     }
-    if (o.k) insert_candidates(valid && better(s, doc, thr_s, thr_d), doc, s, lane, (int)o.k);
+    if (o.full_q) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) capture(o, (some >> j) & 1u, doc[j], sc[j], lane);
+    }
+    if (o.k && __any_sync(0xffffffffu, best >= thr_s)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        insert_candidates(((some >> j) & 1u) && better(sc[j], doc[j], thr_s, thr_d), doc[j], sc[j], lane, (int)o.k);
+    }
+  }
+
+  __device__ __forceinline__ void capture(const Outputs& o, bool valid, uint32_t doc, double s, int lane) {
+    uint32_t m = __ballot_sync(0xffffffffu, valid);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(o.full_count, (unsigned long long)__popc(m));
+      base = shfl_u64(base, 0);
+      unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+      if (valid && pos < o.full_cap) { o.full_q[pos] = q; o.full_doc[pos] = doc; o.full_score[pos] = s; }
+    }
   }
 
   // owned: this warp saw every row of the query, so it may write the final top-k itself.
@@ -320,23 +355,26 @@ __global__ void descend_kernel(IndexView ix, const uint8_t* __restrict__ term_by
 // count_documents (index.rs:282-297) for every term: live occurrence count
 // df_live(t) = sum over the term's rows whose doc is live of sum_x tf[x]  (SURVEY §3.4 rule 2).
 template <int F>
-__global__ void live_df_kernel(IndexView ix, unsigned long long* __restrict__ df_live) {
+__global__ void live_df_kernel(IndexView ix, unsigned long long* __restrict__ df_live,
+                               uint32_t* __restrict__ live_rows) {
   int lane = threadIdx.x & 31;
   uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t t = warp; t < ix.n_terms; t += nwarps) {
     uint64_t a = ix.term_row_begin[t], b = ix.term_row_begin[t + 1];
-    unsigned long long s = 0;
+    unsigned long long s = 0, n = 0;
     for (uint64_t r = a + lane; r < b; r += 32) {
       uint32_t d = ix.post_doc[r];
       bool live = !((ix.removed[d >> 5] >> (d & 31)) & 1u);
       if (live) {
+        ++n;
 #pragma unroll
         for (int f = 0; f < F; ++f) s += ix.post_tf[f][r];
       }
     }
     s = warp_sum_u64(s);
-    if (lane == 0) df_live[t] = s;
+    n = warp_sum_u64(n);
+    if (lane == 0) { df_live[t] = s; live_rows[t] = (uint32_t)n; }
   }
 }
 
@@ -364,9 +402,10 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
                                   const uint32_t* __restrict__ qt_len, Seg* __restrict__ seg_s,
                                   unsigned long long* __restrict__ s_tiles, unsigned long long* __restrict__ qt_gcount,
                                   uint32_t* __restrict__ qt_q, unsigned long long* __restrict__ q_isg,
-                                  unsigned long long* __restrict__ q_grows) {
+                                  unsigned long long* __restrict__ q_grows, unsigned long long* __restrict__ stats) {
   uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (q >= n_queries) return;
+  unsigned long long st_rows = 0, st_live = 0, st_ptr = 0;
+  if (q < n_queries) {
   uint64_t t0 = query_term_off[q], t1 = query_term_off[q + 1];
   uint32_t nl = 0;
   uint64_t rows = 0;
@@ -389,6 +428,10 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
     s.row_begin = a; s.n_rows = (uint32_t)(b - a); s.term = term; s.qlen = qt_len[single];
     s.qti = (uint16_t)(single - t0);
     tiles = ((b + TILE_ROWS - 1) / TILE_ROWS) - (a / TILE_ROWS);
+    // the launch's row statistics are known without touching a row:
+    st_rows = b - a;                       // rows streamed
+    st_live = ix.term_live_rows[term];     // rows whose doc is live = score() evaluations
+    st_ptr = ix.term_df_live[term];        // reference DocumentPointer visits (sum of multiplicities)
   }
   seg_s[q] = s;
   s_tiles[q] = tiles;
@@ -397,6 +440,13 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
   q_grows[q] = g ? rows : 0ull;
   for (uint64_t t = t0; t < t1; ++t)
     qt_gcount[t] = g ? (unsigned long long)(ix.live_prefix[qt_hi[t]] - ix.live_prefix[qt_lo[t]]) : 0ull;
+  }
+  st_rows = warp_sum_u64(st_rows); st_live = warp_sum_u64(st_live); st_ptr = warp_sum_u64(st_ptr);
+  if ((threadIdx.x & 31) == 0 && st_rows) {
+    atomicAdd(&stats[ST_ROWS_STREAMED], st_rows);
+    atomicAdd(&stats[ST_ROWS_SCORED], st_live);
+    atomicAdd(&stats[ST_POINTER_VISITS], st_ptr);
+  }
 }
 
 // One warp per query term of a class-G query: writes one SECONDARY segment per live expanded
@@ -406,10 +456,11 @@ __global__ void gfill_kernel(IndexView ix, uint64_t n_qterms, const uint64_t* __
                              const uint32_t* __restrict__ qt_len, const uint32_t* __restrict__ qt_q,
                              const unsigned long long* __restrict__ qt_gcount, const unsigned long long* __restrict__ qt_goff,
                              Seg* __restrict__ seg_g, unsigned long long* __restrict__ g_tiles,
-                             unsigned long long* __restrict__ q_prim) {
+                             unsigned long long* __restrict__ q_prim, unsigned long long* __restrict__ stats) {
   int lane = threadIdx.x & 31;
   uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long st_rows = 0, st_live = 0, st_ptr = 0;
   for (uint64_t t = warp; t < n_qterms; t += nwarps) {
     if (qt_gcount[t] == 0) continue;
     uint32_t lo = qt_lo[t], hi = qt_hi[t], q = qt_q[t];
@@ -431,12 +482,19 @@ __global__ void gfill_kernel(IndexView ix, uint64_t n_qterms, const uint64_t* __
         g_tiles[idx] = ((b + TILE_ROWS - 1) / TILE_ROWS) - (a / TILE_ROWS);
         unsigned long long cand = ((unsigned long long)(b - a) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
         best = max(best, cand);
+        st_rows += b - a; st_live += ix.term_live_rows[term]; st_ptr += ix.term_df_live[term];
       }
       out += __popc(m);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, (unsigned long long)shfl_u64(best, lane ^ o));
     if (lane == 0 && best) atomicMax(&q_prim[q], best);
+  }
+  st_rows = warp_sum_u64(st_rows); st_live = warp_sum_u64(st_live); st_ptr = warp_sum_u64(st_ptr);
+  if (lane == 0 && st_rows) {
+    atomicAdd(&stats[ST_ROWS_STREAMED], st_rows);
+    atomicAdd(&stats[ST_ROWS_SCORED], st_live);
+    atomicAdd(&stats[ST_POINTER_VISITS], st_ptr);
   }
 }
 
@@ -527,8 +585,52 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(ScoreParams P, int cl
 // 128 consecutive posting rows (aligned), each lane loads 4 rows of every column with one
 // 128-bit streaming load (fully coalesced 512 B per column per warp).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t u4c(const uint4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+
+// BM25::score (bm25.rs:60-93) for the 4 rows of a lane:  score += ((tf' * idf) * boost[x]) * eb.
+// TABFULL: every (tf, fl) of the index is inside the shared-memory table of tf' (no range check,
+// no division in the loop).  SIMPLE: all boosts and the expansion boost are exactly 1.0, so the
+// two multiplications by 1.0 (exact identities) are skipped.
+template <int F, bool TABFULL, bool SIMPLE>
+__device__ __forceinline__ void bm25_rows(const ScoreParams& P, const double* __restrict__ s_tab, const uint4 (&tq)[F],
+                                          const uint4 (&lq)[F], double idf, double ebst, double (&sc)[4]) {
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const double* tab = s_tab + P.tab_off[f];
+    const uint32_t flcap = P.tab_flcap[f];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t tf = u4c(tq[f], j), fl = u4c(lq[f], j);
+      double tfn;
+      if (TABFULL) tfn = tab[tf * flcap + fl];
+      else tfn = (tf < P.tab_tfcap[f] && fl < flcap) ? tab[tf * flcap + fl] : bm25_tf_slow(P, tf, fl, f);
+      double c = __dmul_rn(tfn, idf);
+      if (!SIMPLE) c = __dmul_rn(__dmul_rn(c, P.boost[f]), ebst);
+      if (f == 0) sc[j] = tf > 0 ? c : 0.0;
+      else if (tf > 0) sc[j] = __dadd_rn(sc[j], c);
+    }
+  }
+}
+
+// Single-event ZeroToOne (score() + finalize(), zero_to_one.rs:44-126): max over fields of
+// min(s/tf, 1) * tf / max(field_length, query_terms_len), floored at 0.
+template <int F>
+__device__ __forceinline__ void z2o_rows(const uint4 (&tq)[F], const uint4 (&lq)[F], double zs, uint32_t qtl,
+                                         double (&sc)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sc[j] = 0.0;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t tf = u4c(tq[f], j), fl = u4c(lq[f], j);
+      if (tf > 0) sc[j] = fmax(z2o_entry(zs, tf, fl, qtl), sc[j]);
+    }
+  }
+}
+
 template <int F, int SCORER, bool GMODE>
-__global__ void __launch_bounds__(CTA_THREADS) score_kernel(const __grid_constant__ ScoreParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? 3 : 2)) score_kernel(const __grid_constant__ ScoreParams P) {
   extern __shared__ double s_tab[];
   if (SCORER == 0) {
     for (uint32_t i = threadIdx.x; i < P.tab_total; i += blockDim.x) s_tab[i] = P.tab[i];
@@ -547,7 +649,8 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(const __grid_constan
   WarpAcc acc;
   acc.reset(NONE);
   bool acc_owned = false;
-  uint64_t st_stream = 0, st_scored = 0, st_ptr = 0, st_div = 0;
+  uint32_t st_div = 0;
+  const bool has_removed = P.ix.has_removed != 0;
 
   while (t < span1) {
     const Seg sg = P.segs[s];
@@ -564,9 +667,11 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(const __grid_constan
       const uint32_t explen = P.ix.term_byte_len[sg.term];
       double idf = 0.0, ebst = 1.0, zs = 0.0;
       uint32_t qtl = 0;
+      bool simple = false;
       if (SCORER == 0) {
         idf = P.ix.term_idf[sg.term];
         ebst = P.ix.eb[explen - sg.qlen];
+        simple = P.boosts_all_one && ebst == 1.0;
       } else {
         zs = z2o_term_score(explen, sg.qlen);
         qtl = (uint32_t)(P.query_term_off[sg.q + 1] - P.query_term_off[sg.q]);
@@ -576,8 +681,9 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(const __grid_constan
       const uint32_t* bm = GMODE ? (P.bitmap + (size_t)sg.slot * P.bitmap_words) : nullptr;
 
       for (; t < tend; ++t) {
-        const uint64_t row0 = (abs0 + (t - st0)) * TILE_ROWS + lane * 4;
-        uint4 dq = ldg_stream(P.ix.post_doc + row0);
+        const uint64_t tile_row = (abs0 + (t - st0)) * TILE_ROWS;
+        const uint64_t row0 = tile_row + lane * 4;
+        const uint4 dq = ldg_stream(P.ix.post_doc + row0);
         uint4 tq[F], lq[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
@@ -585,71 +691,86 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(const __grid_constan
           lq[f] = ldg_stream(P.ix.post_fl[f] + row0);
         }
         const uint32_t dv[4] = {dq.x, dq.y, dq.z, dq.w};
+        // rows of this tile that belong to the segment (edge tiles are shared with neighbours)
+        uint32_t valid = 0xFu;
+        if (tile_row < rbeg || tile_row + TILE_ROWS > rend) {
+          const uint32_t lo = tile_row < rbeg ? (uint32_t)(rbeg - tile_row) : 0u;
+          const uint32_t hi = tile_row + TILE_ROWS > rend ? (uint32_t)(rend - tile_row) : (uint32_t)TILE_ROWS;
+          valid = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint64_t row = row0 + j;
-          const uint32_t doc = dv[j];
-          bool in = row >= rbeg && row < rend;
-          bool live = in;
-          if (P.ix.has_removed && in) live = !((__ldg(&P.ix.removed[doc >> 5]) >> (doc & 31)) & 1u);
-          st_stream += in;
-          st_scored += live;
-          double score = 0.0;
-          uint32_t mult = 0;
-#pragma unroll
-          for (int f = 0; f < F; ++f) {
-            const uint32_t tf = (j == 0) ? tq[f].x : (j == 1) ? tq[f].y : (j == 2) ? tq[f].z : tq[f].w;
-            const uint32_t fl = (j == 0) ? lq[f].x : (j == 1) ? lq[f].y : (j == 2) ? lq[f].z : lq[f].w;
-            mult += tf;
-            if (SCORER == 0) {
-              // BM25::score, bm25.rs:60-93: score += tf' * idf * boost[x] * expansion_boost
-              double tfn;
-              if (tf < P.tab_tfcap[f] && fl < P.tab_flcap[f]) tfn = s_tab[P.tab_off[f] + tf * P.tab_flcap[f] + fl];
-              else tfn = bm25_tf_slow(P, tf, fl, f);
-              double c = __dmul_rn(__dmul_rn(__dmul_rn(tfn, idf), P.boost[f]), ebst);
-              if (tf > 0) score = __dadd_rn(score, c);
-            } else {
-              // single-event ZeroToOne: score() + finalize(), zero_to_one.rs:44-126
-              if (tf > 0) score = fmax(z2o_entry(zs, tf, fl, qtl), score);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t r = lane * 4 + j;
+            valid |= (r >= lo && r < hi) ? (1u << j) : 0u;
           }
-          if (live) st_ptr += mult;
-          bool some = live && (SCORER == 0 ? (score > 0.0) : true);
-          if (GMODE) {
-            bool divert = live && (sg.mode == MODE_SECONDARY ||
-                                   ((__ldg(&bm[doc >> 5]) >> (doc & 31)) & 1u));
-            uint32_t m = __ballot_sync(0xffffffffu, divert);
-            if (m) {
-              uint32_t base = 0;
-              if (lane == 0) base = atomicAdd(P.rec_count, (uint32_t)__popc(m));
-              base = __shfl_sync(0xffffffffu, base, 0);
-              uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-              if (divert) {
+        }
+        if (has_removed) {      // removed-but-not-vacuumed docs are skipped (query.rs:65)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (((valid >> j) & 1u) && ((__ldg(&P.ix.removed[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) valid &= ~(1u << j);
+        }
+        double sc[4];
+        uint32_t some = valid;
+        if (SCORER == 0) {
+          if (P.tab_full) {
+            if (simple) bm25_rows<F, true, true>(P, s_tab, tq, lq, idf, ebst, sc);
+            else bm25_rows<F, true, false>(P, s_tab, tq, lq, idf, ebst, sc);
+          } else {
+            bm25_rows<F, false, false>(P, s_tab, tq, lq, idf, ebst, sc);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (!(sc[j] > 0.0)) some &= ~(1u << j);      // Some(score) only if score > 0 (bm25.rs:89-92)
+        } else {
+          z2o_rows<F>(tq, lq, zs, qtl, sc);
+        }
+        if (GMODE) {
+          // rows that must take the ordered per-doc fold instead: every live row of a secondary
+          // list (scored or not: a None still marks the doc visited, query.rs:87), and the rows
+          // of the primary list whose doc also occurs in a secondary list
+          uint32_t dmask = valid;
+          if (sg.mode != MODE_SECONDARY) {
+            dmask = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (((valid >> j) & 1u) && ((__ldg(&bm[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) dmask |= 1u << j;
+          }
+          some &= ~dmask;
+          if (__any_sync(0xffffffffu, dmask != 0)) {
+            const uint32_t c = __popc(dmask);
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(P.rec_count, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t pos = base + incl - c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if ((dmask >> j) & 1u) {
                 if (pos < P.rec_cap) {
-                  P.rec_key[pos] = ((unsigned long long)sg.slot << P.doc_bits) | doc;
-                  P.rec_val[pos] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)row;
+                  P.rec_key[pos] = ((unsigned long long)sg.slot << P.doc_bits) | dv[j];
+                  P.rec_val[pos] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)(row0 + j);
                 } else {
                   atomicOr(P.out.error_flag, 2u);
                 }
+                ++pos;
               }
-              st_div += divert;
             }
-            some = some && !divert;
+            st_div += c;
           }
-          acc.add(P.out, some, doc, score, lane);
         }
+        acc.add4(P.out, some, dv, sc, lane);
       }
     }
     ++s;
   }
   if (acc.q != NONE) acc.flush(P.out, acc_owned, lane);
-  st_stream = warp_sum_u64(st_stream); st_scored = warp_sum_u64(st_scored);
-  st_ptr = warp_sum_u64(st_ptr); st_div = warp_sum_u64(st_div);
-  if (lane == 0) {
-    atomicAdd(&P.stats[ST_ROWS_STREAMED], (unsigned long long)st_stream);
-    atomicAdd(&P.stats[ST_ROWS_SCORED], (unsigned long long)st_scored);
-    atomicAdd(&P.stats[ST_POINTER_VISITS], (unsigned long long)st_ptr);
-    atomicAdd(&P.stats[ST_ROWS_DIVERTED], (unsigned long long)st_div);
+  if (GMODE) {
+    unsigned long long d = warp_sum_u64(st_div);
+    if (lane == 0 && d) atomicAdd(&P.stats[ST_ROWS_DIVERTED], d);
   }
 }
 

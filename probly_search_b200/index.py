@@ -328,6 +328,12 @@ class DeviceBatch:
         capi.check(self._L.pb_batch_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def device_results(self) -> capi.QueryResults:
+        """Device pointers of the result buffers (for the NCCL top-k gather)."""
+        r = capi.QueryResults()
+        capi.check(self._L.pb_batch_device_results(self._h, C.byref(r)))
+        return r
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.pb_batch_destroy(self._h)
