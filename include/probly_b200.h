@@ -171,8 +171,8 @@ typedef struct pb_query_batch_desc {
 /* Per-query outputs.  Any pointer may be NULL (that output is skipped).
  * Digests (order independent, wrap-around sums over the result set):
  *   a(d)        = x = (u32)(d+1) * 0x9E3779B1; x ^= x >> 16                       (32-bit)
- *   doc_digest  = sum (u64)a(d) * 0xD6E8FEB9
- *   score_digest= sum (u64)y * 0xC2B2AE3D,  y = lo(s) ^ hi(s)*0x85EBCA77 ^ a(d); y ^= y >> 15
+ *   doc_digest  = sum over the result set of a(d)                                  (64-bit sum)
+ *   score_digest= sum of y,  y = lo(s) ^ hi(s)*0x85EBCA77 ^ a(d); y ^= y >> 15     (64-bit sum)
  *                 (lo/hi = the two 32-bit halves of the f64 score's bit pattern)
  * top-k rows are ordered (score desc, doc ordinal asc) — the reference's comparison rule
  * (src/lib.rs:54-58) when ordinals follow key order. */

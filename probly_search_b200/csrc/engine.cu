@@ -266,7 +266,7 @@ int batch_build_table(pb_batch* b) {
   for (uint32_t f = 0; f < ix->F; ++f) {
     b->tab_tfcap[f] = tfc[f]; b->tab_flcap[f] = flc[f]; b->tab_off[f] = off;
     for (uint32_t tf = 0; tf < tfc[f]; ++tf)
-      for (uint32_t fl = 0; fl < flc[f]; ++fl) h.push_back(bm25_tf_host(b->k1, b->b, ix->avg[f], tf, fl));
+      for (uint32_t fl = 0; fl < flc[f]; ++fl) h.push_back(tf == 0 ? 0.0 : bm25_tf_host(b->k1, b->b, ix->avg[f], tf, fl));
     off += tfc[f] * flc[f];
   }
   b->tab_total = off;

@@ -135,18 +135,15 @@ __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
   return r;
 }
 
-// Digest hashes (include/probly_b200.h "Digests"): cheap on purpose, they run once per result.
+// Digest terms (include/probly_b200.h "Digests"): cheap on purpose, they run once per result.
 __device__ __forceinline__ uint32_t doc_mix(uint32_t doc) {
   uint32_t a = (doc + 1u) * 0x9E3779B1u;
   return a ^ (a >> 16);
 }
-__device__ __forceinline__ uint64_t doc_hash_from_mix(uint32_t a) { return (uint64_t)a * 0xD6E8FEB9u; }
-__device__ __forceinline__ uint64_t doc_hash(uint32_t doc) { return doc_hash_from_mix(doc_mix(doc)); }
-__device__ __forceinline__ uint64_t score_hash_from_mix(uint32_t a, double s) {
+__device__ __forceinline__ uint32_t score_mix(uint32_t a, double s) {
   uint32_t lo = (uint32_t)__double2loint(s), hi = (uint32_t)__double2hiint(s);
   uint32_t y = lo ^ (hi * 0x85EBCA77u) ^ a;
-  y ^= y >> 15;
-  return (uint64_t)y * 0xC2B2AE3Du;
+  return y ^ (y >> 15);
 }
 
 __device__ __forceinline__ bool better(double as, uint32_t ad, double bs, uint32_t bd) {
@@ -228,8 +225,8 @@ struct WarpAcc {
     if (valid) {
       ++cnt;
       uint32_t a = doc_mix(doc);
-      dd += doc_hash_from_mix(a);
-      sd += score_hash_from_mix(a, s);
+      dd += a;
+      sd += score_mix(a, s);
     }
     if (o.full_q) capture(o, valid, doc, s, lane);
     if (o.k) insert_candidates(valid && better(s, doc, thr_s, thr_d), doc, s, lane, (int)o.k);
@@ -241,21 +238,20 @@ struct WarpAcc {
   __device__ __forceinline__ void add4(const Outputs& o, uint32_t some, const uint32_t (&doc)[4],
                                        const double (&sc)[4], int lane) {
     cnt += __popc(some);
-    double best = -2.0;
+    bool hit = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if ((some >> j) & 1u) {
-        uint32_t a = doc_mix(doc[j]);
-        dd += doc_hash_from_mix(a);
-        sd += score_hash_from_mix(a, sc[j]);
-        best = fmax(best, sc[j]);
-      }
+      const uint32_t m = 0u - ((some >> j) & 1u);          // all ones when the row produced a result
+      const uint32_t a = doc_mix(doc[j]);
+      dd += a & m;
+      sd += score_mix(a, sc[j]) & m;
+      hit |= (m != 0u) && (sc[j] >= thr_s);
     }
     if (o.full_q) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) capture(o, (some >> j) & 1u, doc[j], sc[j], lane);
     }
-    if (o.k && __any_sync(0xffffffffu, best >= thr_s)) {
+    if (o.k && __any_sync(0xffffffffu, hit)) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         insert_candidates(((some >> j) & 1u) && better(sc[j], doc[j], thr_s, thr_d), doc[j], sc[j], lane, (int)o.k);
@@ -606,8 +602,14 @@ __device__ __forceinline__ void bm25_rows(const ScoreParams& P, const double* __
       else tfn = (tf < P.tab_tfcap[f] && fl < flcap) ? tab[tf * flcap + fl] : bm25_tf_slow(P, tf, fl, f);
       double c = __dmul_rn(tfn, idf);
       if (!SIMPLE) c = __dmul_rn(__dmul_rn(c, P.boost[f]), ebst);
-      if (f == 0) sc[j] = tf > 0 ? c : 0.0;
-      else if (tf > 0) sc[j] = __dadd_rn(sc[j], c);
+      if (TABFULL) {
+        // table rows for tf = 0 hold +0.0 and idf / boosts / eb are finite, so c = +-0.0 there and
+        // adding it is an exact identity: no select needed (the reference skips tf = 0, bm25.rs:73)
+        if (f == 0) sc[j] = c; else sc[j] = __dadd_rn(sc[j], c);
+      } else {
+        if (f == 0) sc[j] = tf > 0 ? c : 0.0;
+        else if (tf > 0) sc[j] = __dadd_rn(sc[j], c);
+      }
     }
   }
 }
