@@ -101,8 +101,13 @@ int pb_builder_get_info(const pb_builder* b, pb_builder_info* out);
  *     prefix (query.rs:109-147) are the contiguous, already ordered term range
  *     [node_term_lo, node_term_hi).  Edges of a node are stored sorted by char (lookup only).
  *   - postings: one row per (term, doc), rows of a term contiguous, terms in DFS order, docs
- *     ascending by ordinal inside a term; structure-of-arrays columns doc / tf[f] / fl[f],
- *     every column padded to a multiple of 128 rows (pad rows are zero).
+ *     ascending by ordinal inside a term.  Columns doc / tf[0..F) / fl[0..F) are stored
+ *     TILE-BLOCKED: rows are cut into tiles of 128 and a tile is one contiguous block of
+ *     (1 + 2F) x 128 u32 = [doc x128][tf0 x128]..[tfF-1 x128][fl0 x128]..[flF-1 x128], so a
+ *     tile is a single 512(1+2F)-byte stream (one TMA bulk copy) and every column slice of it
+ *     is a coalesced 512 B line group.  Row r, column c lives at
+ *     post_blocks[((r / 128) * (1 + 2F) + c) * 128 + r % 128].  The row space is padded to
+ *     whole tiles plus one spare tile (pad rows are zero).
  *   - live state: removed-but-not-vacuumed bitmap, live doc count, per-field average. */
 typedef struct pb_index_image {
   uint32_t version;     /* = 1 */
@@ -121,9 +126,7 @@ typedef struct pb_index_image {
   const uint64_t* term_row_begin;  /* [n_terms + 1] */
   const uint32_t* term_byte_len;   /* [n_terms] UTF-8 byte length (bm25.rs:51-52, zero_to_one.rs:57-58) */
   const uint32_t* term_node;       /* [n_terms] */
-  const uint32_t* post_doc;        /* [n_rows_padded] */
-  const uint32_t* post_tf[PB_MAX_FIELDS];
-  const uint32_t* post_fl[PB_MAX_FIELDS];
+  const uint32_t* post_blocks;     /* [n_rows_padded / 128][1 + 2F][128] tile-blocked columns */
   const uint64_t* doc_key;         /* [n_docs] ordinal -> caller's key */
   const uint32_t* removed_bitmap;  /* [(n_docs + 31) / 32] bit set = not live */
   uint64_t n_removed;
@@ -170,9 +173,9 @@ typedef struct pb_query_batch_desc {
 
 /* Per-query outputs.  Any pointer may be NULL (that output is skipped).
  * Digests (order independent, wrap-around sums over the result set):
- *   a(d)        = x = (u32)(d+1) * 0x9E3779B1; x ^= x >> 16                       (32-bit)
+ *   a(d)        = x = (u32)(d+1) * 0x9E3779B1; x ^= x >> 16; x >>= 2              (30-bit)
  *   doc_digest  = sum over the result set of a(d)                                  (64-bit sum)
- *   score_digest= sum of y,  y = lo(s) ^ hi(s)*0x85EBCA77 ^ a(d); y ^= y >> 15     (64-bit sum)
+ *   score_digest= sum of y,  y = lo(s) ^ hi(s)*0x85EBCA77 ^ a(d); y ^= y >> 15; y >>= 2 (64-bit sum)
  *                 (lo/hi = the two 32-bit halves of the f64 score's bit pattern)
  * top-k rows are ordered (score desc, doc ordinal asc) — the reference's comparison rule
  * (src/lib.rs:54-58) when ordinals follow key order. */

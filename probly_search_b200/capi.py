@@ -49,7 +49,7 @@ class IndexImage(C.Structure):
                 ("node_edge_begin", u32p), ("node_term_lo", u32p), ("node_term_hi", u32p),
                 ("node_parent", u32p), ("node_char", u32p), ("edge_char", u32p), ("edge_child", u32p),
                 ("term_row_begin", u64p), ("term_byte_len", u32p), ("term_node", u32p),
-                ("post_doc", u32p), ("post_tf", u32p * PB_MAX_FIELDS), ("post_fl", u32p * PB_MAX_FIELDS),
+                ("post_blocks", u32p),
                 ("doc_key", u64p), ("removed_bitmap", u32p), ("n_removed", C.c_uint64),
                 ("n_live_docs", C.c_uint64), ("field_avg", C.c_double * PB_MAX_FIELDS)]
 
@@ -90,7 +90,7 @@ EXPORTS = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libprobly_b200.so")
+LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(_HERE, "_lib", "libprobly_b200.so")   # PB_LIB_PATH: tuning variants
 _lib = None
 
 

@@ -204,7 +204,7 @@ struct Builder {
   std::vector<uint32_t> f_edge_char, f_edge_child;
   std::vector<uint64_t> f_term_row_begin;
   std::vector<uint32_t> f_term_byte_len, f_term_node;
-  std::vector<uint32_t> f_post_doc, f_post_tf[PB_MAX_FIELDS], f_post_fl[PB_MAX_FIELDS];
+  std::vector<uint32_t> f_post_blocks;   // tile-blocked columns, see pb_index_image
   std::vector<uint32_t> f_removed;
   pb_index_image image{};
 
@@ -465,21 +465,19 @@ struct Builder {
     const uint64_t NR = f_term_row_begin[NT];
     if (NR != log.size()) { set_error("flatten: internal row count mismatch"); return PB_ERR_INVALID; }
     const uint64_t NRP = ((NR + 127) / 128 + 1) * 128;     // pad: whole 128-row tiles + one spare tile
-    f_post_doc.assign(NRP, 0);
+    const uint32_t NCOL = 1 + 2 * F;
+    f_post_blocks.assign(NRP * NCOL, 0);
     uint32_t max_tf[PB_MAX_FIELDS] = {0, 0, 0, 0}, max_fl[PB_MAX_FIELDS] = {0, 0, 0, 0};
-    for (uint32_t f = 0; f < PB_MAX_FIELDS; ++f) {
-      if (f < F) { f_post_tf[f].assign(NRP, 0); f_post_fl[f].assign(NRP, 0); }
-      else { f_post_tf[f].clear(); f_post_fl[f].clear(); }
-    }
     {
       std::vector<uint64_t> fill(f_term_row_begin.begin(), f_term_row_begin.end() - 1);
       for (const Tuple& tp : log) {
         uint64_t r = fill[ord_of[tp.term]]++;
-        f_post_doc[r] = tp.doc;
+        uint32_t* blk = f_post_blocks.data() + (r / 128) * (uint64_t)NCOL * 128 + (r % 128);
+        blk[0] = tp.doc;
         for (uint32_t f = 0; f < F; ++f) {
           uint32_t fl = doc_fl[size_t(tp.doc) * F + f];
-          f_post_tf[f][r] = tp.tf[f];
-          f_post_fl[f][r] = fl;
+          blk[(1 + f) * 128] = tp.tf[f];
+          blk[(1 + F + f) * 128] = fl;
           max_tf[f] = std::max(max_tf[f], tp.tf[f]);
           max_fl[f] = std::max(max_fl[f], fl);
         }
@@ -507,8 +505,7 @@ struct Builder {
     im.edge_char = f_edge_char.data(); im.edge_child = f_edge_child.data();
     im.term_row_begin = f_term_row_begin.data();
     im.term_byte_len = f_term_byte_len.data(); im.term_node = f_term_node.data();
-    im.post_doc = f_post_doc.data();
-    for (uint32_t f = 0; f < F; ++f) { im.post_tf[f] = f_post_tf[f].data(); im.post_fl[f] = f_post_fl[f].data(); }
+    im.post_blocks = f_post_blocks.data();
     im.doc_key = doc_key.data();
     im.removed_bitmap = f_removed.data();
     im.n_removed = nrem;

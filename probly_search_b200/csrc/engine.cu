@@ -94,7 +94,7 @@ struct pb_index {
   uint32_t max_term_bytes = 0, max_tf[4] = {0, 0, 0, 0}, max_fl[4] = {0, 0, 0, 0};
   DBuf<uint32_t> node_edge_begin, node_term_lo, node_term_hi, edge_char, edge_child;
   DBuf<uint64_t> term_row_begin;
-  DBuf<uint32_t> term_byte_len, post_doc, post_tf[4], post_fl[4], removed, live_prefix, term_live_rows;
+  DBuf<uint32_t> term_byte_len, post_blocks, removed, live_prefix, term_live_rows;
   DBuf<uint64_t> term_df_live, liverows_prefix;
   DBuf<double> term_idf, eb;
   // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
@@ -110,8 +110,7 @@ struct pb_index {
     v.node_edge_begin = node_edge_begin.p; v.node_term_lo = node_term_lo.p; v.node_term_hi = node_term_hi.p;
     v.edge_char = edge_char.p; v.edge_child = edge_child.p;
     v.term_row_begin = term_row_begin.p; v.term_byte_len = term_byte_len.p;
-    v.post_doc = post_doc.p;
-    for (int f = 0; f < 4; ++f) { v.post_tf[f] = post_tf[f].p; v.post_fl[f] = post_fl[f].p; }
+    v.post_blocks = post_blocks.p;
     v.removed = removed.p;
     v.term_df_live = term_df_live.p; v.term_live_rows = term_live_rows.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
     v.term_idf = term_idf.p; v.eb = eb.p;
@@ -346,13 +345,15 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
 
 template <int F, int SC, bool G>
 int launch_score_t(pb_batch* b, const ScoreParams& P, int grid) {
-  size_t smem = SC == 0 ? (size_t)P.tab_total * sizeof(double) : 0;
+  size_t smem = score_smem_bytes<F>(P.tab_total);
+  CU(cudaFuncSetAttribute(score_kernel<F, SC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_kernel<F, SC, G><<<grid, CTA_THREADS, smem, b->stream>>>(P);
   CU(cudaGetLastError());
   return PB_OK;
 }
 template <int F, int SC, bool G>
 int occupancy_score_t(int* per_sm, size_t smem) {
+  CU(cudaFuncSetAttribute(score_kernel<F, SC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G>, CTA_THREADS, smem));
   return PB_OK;
 }
@@ -376,9 +377,9 @@ int dispatch_fs(uint32_t F, uint32_t scorer, Fn&& fn) {
 }
 
 int launch_score(pb_batch* b, const ScoreParams& P, bool gmode, uint64_t tiles) {
-  const size_t smem = b->scorer == 0 ? (size_t)P.tab_total * sizeof(double) : 0;
   return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
     constexpr int F = decltype(f)::value, SC = decltype(sc)::value;
+    const size_t smem = score_smem_bytes<F>(P.tab_total);
     int per_sm = 1;
     if (gmode) RC((occupancy_score_t<F, SC, true>(&per_sm, smem)));
     else RC((occupancy_score_t<F, SC, false>(&per_sm, smem)));
@@ -390,6 +391,17 @@ int launch_score(pb_batch* b, const ScoreParams& P, bool gmode, uint64_t tiles) 
     if (gmode) return launch_score_t<F, SC, true>(b, P, grid);
     return launch_score_t<F, SC, false>(b, P, grid);
   });
+}
+
+int launch_mark(pb_batch* b, const ScoreParams& P, int grid, int clear) {
+  switch (b->ix->F) {
+    case 1: mark_kernel<1><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
+    case 2: mark_kernel<2><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
+    case 3: mark_kernel<3><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
+    default: mark_kernel<4><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
+  }
+  CU(cudaGetLastError());
+  return PB_OK;
 }
 
 template <int F, int SC>
@@ -409,7 +421,7 @@ int launch_fold(pb_batch* b, const FoldParams& FP) {
 // Side-path capacity knobs (bytes of HBM the workspace may take).
 constexpr uint64_t REC_CAP_DEFAULT = 48ull << 20;       // records per round (x32 B with sort buffers)
 constexpr uint64_t REC_CAP_MAX = 1ull << 31;
-constexpr uint64_t BITMAP_POOL_BYTES = 1ull << 30;
+constexpr uint64_t BITMAP_POOL_BYTES = 6ull << 30;    // per-query doc bitmaps of one round
 
 int batch_run(pb_batch* b) {
   pb_index* ix = b->ix;
@@ -465,7 +477,8 @@ int batch_run(pb_batch* b) {
   struct Round { uint64_t qa, qb, sa, sb, ta, tb, slots, recs; };
   std::vector<Round> rounds;
   const uint32_t doc_bits = bits_for(std::max<uint64_t>(ix->n_docs, 2));
-  const uint32_t bitmap_words = (uint32_t)((ix->n_docs + 31) / 32 + 1);
+  const uint32_t bitmap_sum_words = (uint32_t)(ix->n_docs / 32768 + 1);
+  const uint32_t bitmap_words = bitmap_sum_words + (uint32_t)((ix->n_docs + 31) / 32 + 1);
   uint64_t rec_cap = 0, slot_cap = 0;
   if (n_gsegs) {
     CU(b->seg_g.ensure(n_gsegs + 1));
@@ -538,7 +551,7 @@ int batch_run(pb_batch* b) {
   P.tab_full = b->tab_full ? 1u : 0u;
   P.boosts_all_one = 1u;
   for (uint32_t f = 0; f < ix->F; ++f) if (b->boost[f] != 1.0) P.boosts_all_one = 0u;
-  P.doc_bits = doc_bits; P.bitmap_words = bitmap_words;
+  P.doc_bits = doc_bits; P.bitmap_words = bitmap_words; P.bitmap_sum_words = bitmap_sum_words;
   P.rec_count = b->counters.p + 1;
   CU(cudaEventRecord(b->ev[2], st));
 
@@ -575,7 +588,7 @@ int batch_run(pb_batch* b) {
       gslot_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, (uint32_t)r.qa);
       CU(cudaGetLastError());
       int mgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * 8, (tiles + 15) / 16));
-      mark_kernel<<<mgrid, CTA_THREADS, 0, st>>>(P, 0);
+      RC(launch_mark(b, P, mgrid, 0));
       CU(cudaGetLastError());
       RC(launch_score(b, P, true, tiles));
       launches += 3;
@@ -597,7 +610,7 @@ int batch_run(pb_batch* b) {
         RC(launch_fold(b, FP));
         launches += 2 + (uint32_t)((end_bit + 7) / 8);
       }
-      mark_kernel<<<mgrid, CTA_THREADS, 0, st>>>(P, 1);
+      RC(launch_mark(b, P, mgrid, 1));
       CU(cudaGetLastError());
       ++launches;
       CU(cudaMemsetAsync(b->counters.p + 1, 0, sizeof(uint32_t), st));
@@ -718,11 +731,7 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
     CU(upload(ix->edge_child, im->edge_child, im->n_edges));
     CU(upload(ix->term_row_begin, im->term_row_begin, im->n_terms + 1));
     CU(upload(ix->term_byte_len, im->term_byte_len, im->n_terms));
-    CU(upload(ix->post_doc, im->post_doc, im->n_rows_padded, TILE_ROWS));
-    for (uint32_t f = 0; f < ix->F; ++f) {
-      CU(upload(ix->post_tf[f], im->post_tf[f], im->n_rows_padded, TILE_ROWS));
-      CU(upload(ix->post_fl[f], im->post_fl[f], im->n_rows_padded, TILE_ROWS));
-    }
+    CU(upload(ix->post_blocks, im->post_blocks, im->n_rows_padded * (1 + 2 * ix->F), (size_t)TILE_ROWS * (1 + 2 * ix->F)));
     ix->h_node_parent.assign(im->node_parent, im->node_parent + im->n_nodes);
     ix->h_node_char.assign(im->node_char, im->node_char + im->n_nodes);
     ix->h_term_node.assign(im->term_node, im->term_node + im->n_terms);

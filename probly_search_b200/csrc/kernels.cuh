@@ -28,6 +28,9 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int TILE_ROWS = 128;          // 32 lanes x 4 rows: one 512 B line group per column
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+#ifndef PB_SCORE_MIN_BLOCKS
+#define PB_SCORE_MIN_BLOCKS 3      // resident CTAs per SM the scoring kernel is compiled for (F <= 2)
+#endif
 
 enum SegMode : uint8_t { MODE_DIRECT = 0, MODE_PRIMARY = 1, MODE_SECONDARY = 2 };
 
@@ -53,9 +56,7 @@ struct IndexView {
   const uint32_t* edge_child;
   const uint64_t* term_row_begin;
   const uint32_t* term_byte_len;
-  const uint32_t* post_doc;
-  const uint32_t* post_tf[4];
-  const uint32_t* post_fl[4];
+  const uint32_t* post_blocks;    // tile-blocked columns: [tile][1 + 2F][128] (pb_index_image)
   const uint32_t* removed;        // bitmap, bit set = doc not live
   const uint64_t* term_df_live;
   const uint32_t* term_live_rows; // rows of the term whose doc is live
@@ -68,6 +69,16 @@ struct IndexView {
   uint32_t num_fields;
   uint32_t has_removed;
 };
+
+// Random access into the tile-blocked columns (side path, live_df): column 0 = doc,
+// 1 + f = tf[f], 1 + F + f = fl[f].
+template <int F>
+__device__ __forceinline__ const uint32_t* row_ptr(const uint32_t* blocks, uint64_t row) {
+  return blocks + (row / TILE_ROWS) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + (row % TILE_ROWS);
+}
+template <int F> __device__ __forceinline__ uint32_t row_doc(const uint32_t* b, uint64_t r) { return row_ptr<F>(b, r)[0]; }
+template <int F> __device__ __forceinline__ uint32_t row_tf(const uint32_t* b, uint64_t r, int f) { return row_ptr<F>(b, r)[(1 + f) * TILE_ROWS]; }
+template <int F> __device__ __forceinline__ uint32_t row_fl(const uint32_t* b, uint64_t r, int f) { return row_ptr<F>(b, r)[(1 + F + f) * TILE_ROWS]; }
 
 struct Outputs {
   unsigned long long* n_results;
@@ -115,7 +126,8 @@ struct ScoreParams {
   uint32_t boosts_all_one;       // every fields_boost is exactly 1.0
   // side path
   uint32_t* bitmap;              // [slots][bitmap_words]
-  uint32_t bitmap_words;
+  uint32_t bitmap_words;         // words per slot (summary + doc bits)
+  uint32_t bitmap_sum_words;     // leading summary words of a slot
   unsigned long long* rec_key;
   unsigned long long* rec_val;
   uint32_t* rec_count;
@@ -138,12 +150,12 @@ __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
 // Digest terms (include/probly_b200.h "Digests"): cheap on purpose, they run once per result.
 __device__ __forceinline__ uint32_t doc_mix(uint32_t doc) {
   uint32_t a = (doc + 1u) * 0x9E3779B1u;
-  return a ^ (a >> 16);
+  return (a ^ (a >> 16)) >> 2;          // 30 bits: four terms add up inside 32 bits
 }
 __device__ __forceinline__ uint32_t score_mix(uint32_t a, double s) {
   uint32_t lo = (uint32_t)__double2loint(s), hi = (uint32_t)__double2hiint(s);
   uint32_t y = lo ^ (hi * 0x85EBCA77u) ^ a;
-  return y ^ (y >> 15);
+  return (y ^ (y >> 15)) >> 2;
 }
 
 __device__ __forceinline__ bool better(double as, uint32_t ad, double bs, uint32_t bd) {
@@ -235,19 +247,32 @@ struct WarpAcc {
   // Four rows per lane at once (the scoring kernel's tile shape).  `some` = 4-bit mask of rows
   // that produced a result.  The top-k structure is only touched when some lane holds a score
   // that reaches the current k-th best.
+  template <bool CAPTURE>
   __device__ __forceinline__ void add4(const Outputs& o, uint32_t some, const uint32_t (&doc)[4],
                                        const double (&sc)[4], int lane) {
-    cnt += __popc(some);
     bool hit = false;
+    if (__all_sync(0xffffffffu, some == 0xFu)) {            // the common case: every row produced a result
+      cnt += 4;
+      uint32_t a[4], y[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t m = 0u - ((some >> j) & 1u);          // all ones when the row produced a result
-      const uint32_t a = doc_mix(doc[j]);
-      dd += a & m;
-      sd += score_mix(a, sc[j]) & m;
-      hit |= (m != 0u) && (sc[j] >= thr_s);
+      for (int j = 0; j < 4; ++j) { a[j] = doc_mix(doc[j]); y[j] = score_mix(a[j], sc[j]); hit |= sc[j] >= thr_s; }
+      dd += (a[0] + a[1]) + (a[2] + a[3]);
+      sd += (y[0] + y[1]) + (y[2] + y[3]);
+    } else {
+      cnt += __popc(some);
+      uint32_t sa = 0, sy = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = 0u - ((some >> j) & 1u);          // all ones when the row produced a result
+        const uint32_t a = doc_mix(doc[j]);
+        sa += a & m;
+        sy += score_mix(a, sc[j]) & m;
+        hit |= (m != 0u) && (sc[j] >= thr_s);
+      }
+      dd += sa;
+      sd += sy;
     }
-    if (o.full_q) {
+    if (CAPTURE && o.full_q) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) capture(o, (some >> j) & 1u, doc[j], sc[j], lane);
     }
@@ -360,12 +385,13 @@ __global__ void live_df_kernel(IndexView ix, unsigned long long* __restrict__ df
     uint64_t a = ix.term_row_begin[t], b = ix.term_row_begin[t + 1];
     unsigned long long s = 0, n = 0;
     for (uint64_t r = a + lane; r < b; r += 32) {
-      uint32_t d = ix.post_doc[r];
+      const uint32_t* rp = row_ptr<F>(ix.post_blocks, r);
+      uint32_t d = rp[0];
       bool live = !((ix.removed[d >> 5] >> (d & 31)) & 1u);
       if (live) {
         ++n;
 #pragma unroll
-        for (int f = 0; f < F; ++f) s += ix.post_tf[f][r];
+        for (int f = 0; f < F; ++f) s += rp[(1 + f) * TILE_ROWS];
       }
     }
     s = warp_sum_u64(s);
@@ -540,7 +566,8 @@ __device__ __forceinline__ uint32_t seg_of_tile(const uint64_t* __restrict__ til
 }
 
 // mark (or clear) the docs of SECONDARY segments in the query's bitmap
-__global__ void __launch_bounds__(CTA_THREADS) mark_kernel(ScoreParams P, int clear) {
+template <int F>
+__global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant__ ScoreParams P, int clear) {
   const int lane = threadIdx.x & 31;
   const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -554,19 +581,24 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(ScoreParams P, int cl
     const uint64_t st0 = P.tile_off[s], st1 = P.tile_off[s + 1];
     const uint64_t tend = min(t1, st1);
     if (sg.mode == MODE_SECONDARY) {
-      uint32_t* bm = P.bitmap + (size_t)sg.slot * P.bitmap_words;
+      // slot layout: [summary words: 1 bit per 1024 docs][doc words: 1 bit per doc]
+      uint32_t* sm = P.bitmap + (size_t)sg.slot * P.bitmap_words;
+      uint32_t* bm = sm + P.bitmap_sum_words;
       const uint64_t abs0 = sg.row_begin / TILE_ROWS;
       const uint64_t rend = sg.row_begin + sg.n_rows;
       for (; t < tend; ++t) {
         uint64_t row0 = (abs0 + (t - st0)) * TILE_ROWS + lane * 4;
-        uint4 d = ldg_stream(P.ix.post_doc + row0);
+        uint4 d = ldg_stream(P.ix.post_blocks + (abs0 + (t - st0)) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 4);
         uint32_t dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint64_t row = row0 + j;
           if (row >= sg.row_begin && row < rend) {
-            if (clear) bm[dv[j] >> 5] = 0u;
-            else atomicOr(&bm[dv[j] >> 5], 1u << (dv[j] & 31));
+            if (clear) { bm[dv[j] >> 5] = 0u; sm[dv[j] >> 15] = 0u; }
+            else {
+              atomicOr(&bm[dv[j] >> 5], 1u << (dv[j] & 31));
+              atomicOr(&sm[dv[j] >> 15], 1u << ((dv[j] >> 10) & 31));
+            }
           }
         }
       }
@@ -631,14 +663,231 @@ __device__ __forceinline__ void z2o_rows(const uint4 (&tq)[F], const uint4 (&lq)
   }
 }
 
+// Per-segment state of the scoring loop.
+struct SegCtx {
+  uint64_t rbeg, rend;      // absolute row range of the segment
+  double idf, ebst, zs;     // bm25.rs:35-58 / zero_to_one.rs:72
+  uint32_t qtl;             // query_terms_len (query.rs:32)
+  uint32_t seg;             // segment index (event order key of the side path)
+  uint32_t slot;
+  uint32_t mode;
+  const uint32_t* sum;      // GMODE: the query's summary bits / doc bits
+  const uint32_t* bm;
+};
+
+// One tile = 128 aligned rows; lane l owns rows 4l..4l+3 (one 128-bit load per column).
+//   EDGE : the tile is shared with neighbouring segments -> per-row range mask
+//   FAST : no removed docs, no full-result capture, complete BM25 table -> no per-row checks
+template <int F>
+struct TileRegs {
+  uint4 dq;
+  uint4 tq[F], lq[F];
+};
+template <int F>
+__device__ __forceinline__ void load_tile(const ScoreParams& P, uint64_t tile_row, int lane, TileRegs<F>& R) {
+  // one contiguous (1 + 2F) x 512 B block per tile: a single base address, immediate column offsets
+  const uint32_t* base = P.ix.post_blocks + (tile_row / TILE_ROWS) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 4;
+  R.dq = ldg_stream(base);
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    R.tq[f] = ldg_stream(base + (1 + f) * TILE_ROWS);
+    R.lq[f] = ldg_stream(base + (1 + F + f) * TILE_ROWS);
+  }
+}
+
+template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, bool SIMPLE>
+__device__ __forceinline__ void compute_tile(const ScoreParams& P, const double* __restrict__ s_tab, const SegCtx& C,
+                                             const TileRegs<F>& R, uint64_t tile_row, int lane, WarpAcc& acc,
+                                             uint32_t& st_div) {
+  const uint64_t row0 = tile_row + lane * 4;
+  const uint4 dq = R.dq;
+  const uint4 (&tq)[F] = R.tq;
+  const uint4 (&lq)[F] = R.lq;
+  const uint32_t dv[4] = {dq.x, dq.y, dq.z, dq.w};
+  uint32_t valid = 0xFu;
+  if (EDGE) {
+    const uint32_t lo = tile_row < C.rbeg ? (uint32_t)(C.rbeg - tile_row) : 0u;
+    const uint32_t hi = tile_row + TILE_ROWS > C.rend ? (uint32_t)(C.rend - tile_row) : (uint32_t)TILE_ROWS;
+    valid = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t r = lane * 4 + j;
+      valid |= (r >= lo && r < hi) ? (1u << j) : 0u;
+    }
+  }
+  if (!FAST && P.ix.has_removed) {      // removed-but-not-vacuumed docs are skipped (query.rs:65)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (((valid >> j) & 1u) && ((__ldg(&P.ix.removed[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) valid &= ~(1u << j);
+  }
+  double sc[4];
+  uint32_t some = valid;
+  if (SCORER == 0) {
+    if (FAST) bm25_rows<F, true, SIMPLE>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
+    else if (P.tab_full) bm25_rows<F, true, false>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
+    else bm25_rows<F, false, false>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (!(sc[j] > 0.0)) some &= ~(1u << j);      // Some(score) only if score > 0 (bm25.rs:89-92)
+  } else {
+    z2o_rows<F>(tq, lq, C.zs, C.qtl, sc);
+  }
+  if (GMODE) {
+    // rows that must take the ordered per-doc fold instead: every live row of a secondary list
+    // (scored or not: a None still marks the doc visited, query.rs:87), and the rows of the
+    // primary list whose doc also occurs in a secondary list
+    uint32_t dmask = valid;
+    if (C.mode != MODE_SECONDARY) {
+      dmask = 0;
+      bool maybe = true;
+      if (!EDGE) {
+        // docs ascend inside a list: the tile covers [first, last]; consult the 1024-doc summary bits
+        const uint32_t b0 = __shfl_sync(0xffffffffu, dv[0], 0) >> 10, b1 = __shfl_sync(0xffffffffu, dv[3], 31) >> 10;
+        if ((b0 >> 5) == (b1 >> 5)) {
+          const uint32_t w = __ldg(&C.sum[b0 >> 5]);
+          const uint32_t mask = (0xFFFFFFFFu >> (31u - (b1 & 31u))) & (0xFFFFFFFFu << (b0 & 31u));
+          maybe = (w & mask) != 0u;
+        }
+      }
+      if (maybe) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (((valid >> j) & 1u) && ((__ldg(&C.bm[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) dmask |= 1u << j;
+      }
+    }
+    some &= ~dmask;
+    if (__any_sync(0xffffffffu, dmask != 0)) {
+      const uint32_t c = __popc(dmask);
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      uint32_t base = 0;
+      if (lane == 31) base = atomicAdd(P.rec_count, incl);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      uint32_t pos = base + incl - c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((dmask >> j) & 1u) {
+          if (pos < P.rec_cap) {
+            P.rec_key[pos] = ((unsigned long long)C.slot << P.doc_bits) | dv[j];
+            P.rec_val[pos] = ((unsigned long long)C.seg << 32) | (unsigned long long)(uint32_t)(row0 + j);
+          } else {
+            atomicOr(P.out.error_flag, 2u);
+          }
+          ++pos;
+        }
+      }
+      st_div += c;
+    }
+  }
+  if (FAST) acc.template add4<false>(P.out, some, dv, sc, lane);
+  else acc.template add4<true>(P.out, some, dv, sc, lane);
+}
+
+template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, bool SIMPLE>
+__device__ __forceinline__ void process_tile(const ScoreParams& P, const double* __restrict__ s_tab, const SegCtx& C,
+                                             uint64_t tile_row, int lane, WarpAcc& acc, uint32_t& st_div) {
+  TileRegs<F> R;
+  load_tile<F>(P, tile_row, lane, R);
+  compute_tile<F, SCORER, GMODE, EDGE, FAST, SIMPLE>(P, s_tab, C, R, tile_row, lane, acc, st_div);
+}
+
+// Interior tiles [t, ib) of one segment, software-pipelined: the loads of tile i+1 are in flight
+// while tile i is scored (PB_PREFETCH), so a warp never sits idle on its own L2/HBM latency.
+#ifndef PB_PREFETCH
+#define PB_PREFETCH 0
+#endif
+template <int F, int SCORER, bool GMODE, bool FAST, bool SIMPLE>
+__device__ __forceinline__ void interior_tiles(const ScoreParams& P, const double* __restrict__ s_tab, const SegCtx& C,
+                                               uint64_t tile_row, uint32_t n_tiles, int lane, WarpAcc& acc,
+                                               uint32_t& st_div) {
+#if PB_PREFETCH
+  if (n_tiles == 0) return;
+  TileRegs<F> cur;
+  load_tile<F>(P, tile_row, lane, cur);
+  for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS) {
+    TileRegs<F> nxt;
+    // the spare tile at the end of every column makes this load safe even past the last tile
+    load_tile<F>(P, tile_row + TILE_ROWS, lane, nxt);
+    compute_tile<F, SCORER, GMODE, false, FAST, SIMPLE>(P, s_tab, C, cur, tile_row, lane, acc, st_div);
+    cur = nxt;
+  }
+#else
+  for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS)
+    process_tile<F, SCORER, GMODE, false, FAST, SIMPLE>(P, s_tab, C, tile_row, lane, acc, st_div);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA staging.  Every warp runs its own PB_STAGES-deep ring of tiles in shared memory: a tile
+// is ONE contiguous block of (1 + 2F) x 512 B in the tile-blocked layout, fetched with a single
+// cp.async.bulk (1-D TMA) that lands on a per-stage mbarrier; the warp then reads its 4 rows per
+// column with one conflict-free LDS.128 per lane.  Loads in flight cost no registers, so the
+// latency of L2/HBM is hidden by the ring depth instead of by occupancy.
+// ------------------------------------------------------------------------------------------
+#ifndef PB_TMA
+#define PB_TMA 0
+#endif
+#ifndef PB_STAGES
+#define PB_STAGES 3
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int F>
+struct TileRing {
+  static constexpr int NCOL = 1 + 2 * F;
+  static constexpr int COL_BYTES = TILE_ROWS * 4;
+  static constexpr int STAGE_BYTES = NCOL * COL_BYTES;
+  static constexpr int WARP_BYTES = (PB_STAGES * STAGE_BYTES + PB_STAGES * 8 + 127) / 128 * 128;   // + mbarriers
+};
+
 template <int F, int SCORER, bool GMODE>
-__global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? 3 : 2)) score_kernel(const __grid_constant__ ScoreParams P) {
-  extern __shared__ double s_tab[];
+__global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? PB_SCORE_MIN_BLOCKS : 2)) score_kernel(const __grid_constant__ ScoreParams P) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  double* s_tab = reinterpret_cast<double*>(s_raw);
   if (SCORER == 0) {
     for (uint32_t i = threadIdx.x; i < P.tab_total; i += blockDim.x) s_tab[i] = P.tab[i];
-    __syncthreads();
   }
   const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+#if PB_TMA
+  using Ring = TileRing<F>;
+  // ring of this warp: stages, then the stage mbarriers
+  unsigned char* ring = s_raw + ((P.tab_total * 8 + 127) & ~127u) + (size_t)wid * Ring::WARP_BYTES;
+  const uint32_t ring_s = smem_u32(ring);
+  const uint32_t bar_s = ring_s + PB_STAGES * Ring::STAGE_BYTES;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < PB_STAGES; ++i) mbar_init(bar_s + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
+  __syncthreads();
   const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint64_t T = P.tile_end - P.tile_begin;
@@ -652,7 +901,38 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? 3 : 2)) score_kernel(co
   acc.reset(NONE);
   bool acc_owned = false;
   uint32_t st_div = 0;
-  const bool has_removed = P.ix.has_removed != 0;
+  // launch-wide: may the interior tiles take the check-free path?
+  const bool fast = !P.ix.has_removed && P.out.full_q == nullptr && (SCORER != 0 || P.tab_full);
+
+#if PB_TMA
+  // producer cursor: the next tile to fetch (runs PB_STAGES - 1 tiles ahead of the consumer)
+  uint64_t tp = span0;
+  uint32_t sp = s;
+  uint64_t sp_st0 = P.tile_off[sp], sp_st1 = P.tile_off[sp + 1];
+  uint64_t sp_abs0 = P.segs[sp].row_begin / TILE_ROWS;
+  uint32_t n_issued = 0, n_consumed = 0;
+  auto issue = [&]() {
+    while (tp >= sp_st1) {                    // next segment that owns tiles
+      ++sp;
+      sp_st0 = sp_st1;
+      sp_st1 = P.tile_off[sp + 1];
+      sp_abs0 = P.segs[sp].row_begin / TILE_ROWS;
+    }
+    const uint64_t tile_row = (sp_abs0 + (tp - sp_st0)) * TILE_ROWS;
+    const uint32_t stage = n_issued % PB_STAGES;
+    const uint32_t bar = bar_s + 8 * stage;
+    if (lane == 0) {
+      mbar_expect_tx(bar, Ring::STAGE_BYTES);
+      tma_load_1d(ring_s + stage * Ring::STAGE_BYTES,
+                  P.ix.post_blocks + (tile_row / TILE_ROWS) * (uint64_t)(Ring::NCOL * TILE_ROWS), Ring::STAGE_BYTES, bar);
+    }
+    ++tp;
+    ++n_issued;
+  };
+#pragma unroll 1
+  for (int i = 0; i < PB_STAGES - 1; ++i)
+    if (tp < span1) issue();
+#endif
 
   while (t < span1) {
     const Seg sg = P.segs[s];
@@ -665,107 +945,70 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? 3 : 2)) score_kernel(co
         // class S: the query is exactly this segment; it is "owned" when its tiles are all ours
         acc_owned = !GMODE && st0 >= span0 && st1 <= span1;
       }
-      // per-segment constants (before_each, bm25.rs:35-58 / zero_to_one.rs:57-58,72)
+      SegCtx C;
+      C.rbeg = sg.row_begin; C.rend = sg.row_begin + sg.n_rows;
+      C.seg = s; C.slot = sg.slot; C.mode = sg.mode;
+      C.idf = 0.0; C.ebst = 1.0; C.zs = 0.0; C.qtl = 0;
+      C.sum = nullptr; C.bm = nullptr;
       const uint32_t explen = P.ix.term_byte_len[sg.term];
-      double idf = 0.0, ebst = 1.0, zs = 0.0;
-      uint32_t qtl = 0;
       bool simple = false;
       if (SCORER == 0) {
-        idf = P.ix.term_idf[sg.term];
-        ebst = P.ix.eb[explen - sg.qlen];
-        simple = P.boosts_all_one && ebst == 1.0;
+        C.idf = P.ix.term_idf[sg.term];
+        C.ebst = P.ix.eb[explen - sg.qlen];
+        simple = P.boosts_all_one && C.ebst == 1.0;
       } else {
-        zs = z2o_term_score(explen, sg.qlen);
-        qtl = (uint32_t)(P.query_term_off[sg.q + 1] - P.query_term_off[sg.q]);
+        C.zs = z2o_term_score(explen, sg.qlen);
+        C.qtl = (uint32_t)(P.query_term_off[sg.q + 1] - P.query_term_off[sg.q]);
       }
-      const uint64_t abs0 = sg.row_begin / TILE_ROWS;
-      const uint64_t rbeg = sg.row_begin, rend = sg.row_begin + sg.n_rows;
-      const uint32_t* bm = GMODE ? (P.bitmap + (size_t)sg.slot * P.bitmap_words) : nullptr;
-
-      for (; t < tend; ++t) {
-        const uint64_t tile_row = (abs0 + (t - st0)) * TILE_ROWS;
-        const uint64_t row0 = tile_row + lane * 4;
-        const uint4 dq = ldg_stream(P.ix.post_doc + row0);
-        uint4 tq[F], lq[F];
+      if (GMODE) {
+        C.sum = P.bitmap + (size_t)sg.slot * P.bitmap_words;
+        C.bm = C.sum + P.bitmap_sum_words;
+      }
+      const uint64_t abs0 = C.rbeg / TILE_ROWS;
+#if PB_TMA
+      uint64_t tile_row = (abs0 + (t - st0)) * TILE_ROWS;
+      for (; t < tend; ++t, tile_row += TILE_ROWS) {
+        // keep the ring full: fetch the tile PB_STAGES - 1 ahead (its stage was drained last iteration)
+        if (tp < span1) issue();
+        const uint32_t stage = n_consumed % PB_STAGES;
+        mbar_wait(bar_s + 8 * stage, (n_consumed / PB_STAGES) & 1u);
+        ++n_consumed;
+        TileRegs<F> R;
+        const unsigned char* sb = ring + stage * Ring::STAGE_BYTES + lane * 16;
+        R.dq = *reinterpret_cast<const uint4*>(sb);
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          tq[f] = ldg_stream(P.ix.post_tf[f] + row0);
-          lq[f] = ldg_stream(P.ix.post_fl[f] + row0);
+          R.tq[f] = *reinterpret_cast<const uint4*>(sb + (1 + f) * Ring::COL_BYTES);
+          R.lq[f] = *reinterpret_cast<const uint4*>(sb + (1 + F + f) * Ring::COL_BYTES);
         }
-        const uint32_t dv[4] = {dq.x, dq.y, dq.z, dq.w};
-        // rows of this tile that belong to the segment (edge tiles are shared with neighbours)
-        uint32_t valid = 0xFu;
-        if (tile_row < rbeg || tile_row + TILE_ROWS > rend) {
-          const uint32_t lo = tile_row < rbeg ? (uint32_t)(rbeg - tile_row) : 0u;
-          const uint32_t hi = tile_row + TILE_ROWS > rend ? (uint32_t)(rend - tile_row) : (uint32_t)TILE_ROWS;
-          valid = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t r = lane * 4 + j;
-            valid |= (r >= lo && r < hi) ? (1u << j) : 0u;
-          }
-        }
-        if (has_removed) {      // removed-but-not-vacuumed docs are skipped (query.rs:65)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (((valid >> j) & 1u) && ((__ldg(&P.ix.removed[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) valid &= ~(1u << j);
-        }
-        double sc[4];
-        uint32_t some = valid;
-        if (SCORER == 0) {
-          if (P.tab_full) {
-            if (simple) bm25_rows<F, true, true>(P, s_tab, tq, lq, idf, ebst, sc);
-            else bm25_rows<F, true, false>(P, s_tab, tq, lq, idf, ebst, sc);
-          } else {
-            bm25_rows<F, false, false>(P, s_tab, tq, lq, idf, ebst, sc);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (!(sc[j] > 0.0)) some &= ~(1u << j);      // Some(score) only if score > 0 (bm25.rs:89-92)
-        } else {
-          z2o_rows<F>(tq, lq, zs, qtl, sc);
-        }
-        if (GMODE) {
-          // rows that must take the ordered per-doc fold instead: every live row of a secondary
-          // list (scored or not: a None still marks the doc visited, query.rs:87), and the rows
-          // of the primary list whose doc also occurs in a secondary list
-          uint32_t dmask = valid;
-          if (sg.mode != MODE_SECONDARY) {
-            dmask = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (((valid >> j) & 1u) && ((__ldg(&bm[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) dmask |= 1u << j;
-          }
-          some &= ~dmask;
-          if (__any_sync(0xffffffffu, dmask != 0)) {
-            const uint32_t c = __popc(dmask);
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += v;
-            }
-            uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(P.rec_count, incl);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            uint32_t pos = base + incl - c;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if ((dmask >> j) & 1u) {
-                if (pos < P.rec_cap) {
-                  P.rec_key[pos] = ((unsigned long long)sg.slot << P.doc_bits) | dv[j];
-                  P.rec_val[pos] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)(row0 + j);
-                } else {
-                  atomicOr(P.out.error_flag, 2u);
-                }
-                ++pos;
-              }
-            }
-            st_div += c;
-          }
-        }
-        acc.add4(P.out, some, dv, sc, lane);
+        const bool edge = tile_row < C.rbeg || tile_row + TILE_ROWS > C.rend;
+        if (edge) compute_tile<F, SCORER, GMODE, true, false, false>(P, s_tab, C, R, tile_row, lane, acc, st_div);
+        else if (!fast) compute_tile<F, SCORER, GMODE, false, false, false>(P, s_tab, C, R, tile_row, lane, acc, st_div);
+        else if (simple) compute_tile<F, SCORER, GMODE, false, true, true>(P, s_tab, C, R, tile_row, lane, acc, st_div);
+        else compute_tile<F, SCORER, GMODE, false, true, false>(P, s_tab, C, R, tile_row, lane, acc, st_div);
+        __syncwarp();     // every lane has consumed its registers of this stage before it is refilled
       }
+#else
+      // virtual tile range of the segment's fully covered (interior) tiles
+      const uint64_t int0 = st0 + ((C.rbeg % TILE_ROWS) ? 1 : 0);
+      const uint64_t int1 = st1 - ((C.rend % TILE_ROWS) ? 1 : 0);     // may be < int0 for a tiny segment
+      const uint64_t ia = min(max(t, int0), tend), ib = max(min(tend, int1), ia);
+      for (; t < ia; ++t)
+        process_tile<F, SCORER, GMODE, true, false, false>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
+      {
+        const uint64_t row = (abs0 + (t - st0)) * TILE_ROWS;
+        const uint32_t n = (uint32_t)(ib - t);
+        if (fast) {
+          if (simple) interior_tiles<F, SCORER, GMODE, true, true>(P, s_tab, C, row, n, lane, acc, st_div);
+          else interior_tiles<F, SCORER, GMODE, true, false>(P, s_tab, C, row, n, lane, acc, st_div);
+        } else {
+          interior_tiles<F, SCORER, GMODE, false, false>(P, s_tab, C, row, n, lane, acc, st_div);
+        }
+        t = ib;
+      }
+      for (; t < tend; ++t)
+        process_tile<F, SCORER, GMODE, true, false, false>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
+#endif
     }
     ++s;
   }
@@ -774,6 +1017,16 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? 3 : 2)) score_kernel(co
     unsigned long long d = warp_sum_u64(st_div);
     if (lane == 0 && d) atomicAdd(&P.stats[ST_ROWS_DIVERTED], d);
   }
+}
+
+// dynamic shared memory of the scoring kernel: BM25 table + the warps' tile rings
+template <int F>
+inline size_t score_smem_bytes(uint32_t tab_total) {
+  size_t b = ((size_t)tab_total * 8 + 127) & ~(size_t)127;
+#if PB_TMA
+  b += (size_t)WARPS_PER_CTA * TileRing<F>::WARP_BYTES;
+#endif
+  return b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -797,7 +1050,7 @@ __device__ __forceinline__ double bm25_row_score(const ScoreParams& P, const Seg
   double score = 0.0;
 #pragma unroll
   for (int f = 0; f < F; ++f) {
-    uint32_t tf = P.ix.post_tf[f][row], fl = P.ix.post_fl[f][row];
+    uint32_t tf = row_tf<F>(P.ix.post_blocks, row, f), fl = row_fl<F>(P.ix.post_blocks, row, f);
     if (tf > 0) {
       double tfn = (tf < P.tab_tfcap[f] && fl < P.tab_flcap[f]) ? P.tab[P.tab_off[f] + tf * P.tab_flcap[f] + fl]
                                                                  : bm25_tf_slow(P, tf, fl, f);
@@ -883,12 +1136,12 @@ __global__ void __launch_bounds__(CTA_THREADS) fold_kernel(const __grid_constant
               if ((done_lo >> j) & 1ull) continue;
               unsigned long long v = FP.val[i + j];
               uint32_t row = (uint32_t)v;
-              uint32_t tf = P.ix.post_tf[x][row];
+              uint32_t tf = row_tf<F>(P.ix.post_blocks, row, x);
               if (tf == 0) { done_lo |= 1ull << j; continue; }
               const Seg sg = P.segs[(uint32_t)(v >> 32)];
               double sc = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
               if (bj < 0 || sc > bs || (sc == bs && v < bv)) {
-                bj = (int)j; bs = sc; bv = v; btf = tf; bfl = P.ix.post_fl[x][row]; bterm = sg.term; bqti = sg.qti;
+                bj = (int)j; bs = sc; bv = v; btf = tf; bfl = row_fl<F>(P.ix.post_blocks, row, x); bterm = sg.term; bqti = sg.qti;
               }
             }
             if (bj < 0) break;

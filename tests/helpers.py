@@ -23,12 +23,16 @@ def image_arrays(im) -> dict:
         "term_row_begin": as_arr(im.term_row_begin, shape=(nt + 1,)),
         "term_byte_len": as_arr(im.term_byte_len, shape=(nt,)) if nt else np.zeros(0, np.uint32),
         "term_node": as_arr(im.term_node, shape=(nt,)) if nt else np.zeros(0, np.uint32),
-        "post_doc": as_arr(im.post_doc, shape=(nrp,)),
-        "post_tf": [as_arr(im.post_tf[f], shape=(nrp,)) for f in range(F)],
-        "post_fl": [as_arr(im.post_fl[f], shape=(nrp,)) for f in range(F)],
+    }
+    # tile-blocked columns [tile][1 + 2F][128] -> plain per-row columns
+    blocks = as_arr(im.post_blocks, shape=(nrp // 128, 1 + 2 * F, 128))
+    out.update({
+        "post_doc": blocks[:, 0, :].reshape(-1),
+        "post_tf": [blocks[:, 1 + f, :].reshape(-1) for f in range(F)],
+        "post_fl": [blocks[:, 1 + F + f, :].reshape(-1) for f in range(F)],
         "doc_key": as_arr(im.doc_key, shape=(nd,)) if nd else np.zeros(0, np.uint64),
         "removed": as_arr(im.removed_bitmap, shape=((nd + 31) // 32 + 1,)),
-    }
+    })
     return out
 
 
