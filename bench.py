@@ -236,25 +236,20 @@ def main():
     k = args.top_k
     batch = DeviceBatch(ix, fq, calc, cfg.boosts, top_k=k)
 
-    # views over the library's device result buffers for the NCCL gather
-    gather_in = gather_out = None
-
-    class _DevArr:
-        def __init__(self, ptr, shape, typestr):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+    # NCCL gather of the per-query top-k blocks, straight from the library's device result buffers
+    from probly_search_b200 import distributed as D
+    gathered = None
 
     def step_device():
+        nonlocal gathered
         batch.run()
         if world > 1:
-            nonlocal gather_in, gather_out
             dp = batch.device_results()
-            docs = torch.as_tensor(_DevArr(dp.topk_doc, (n_queries * k,), "<i4"), device=f"cuda:{local_rank}")
-            scs = torch.as_tensor(_DevArr(dp.topk_score, (n_queries * k,), "<f8"), device=f"cuda:{local_rank}")
-            if gather_out is None:
-                gather_out = (torch.empty(world * n_queries * k, dtype=torch.int32, device=docs.device),
-                              torch.empty(world * n_queries * k, dtype=torch.float64, device=docs.device))
-            dist.all_gather_into_tensor(gather_out[0], docs)      # NCCL over NVLink: the top-k gather
-            dist.all_gather_into_tensor(gather_out[1], scs)
+            dev = f"cuda:{local_rank}"
+            n = torch.as_tensor(D.DeviceArray(dp.topk_n, (n_queries,), "<i4"), device=dev)
+            docs = torch.as_tensor(D.DeviceArray(dp.topk_doc, (n_queries, k), "<i4"), device=dev)
+            scs = torch.as_tensor(D.DeviceArray(dp.topk_score, (n_queries, k), "<f8"), device=dev)
+            gathered = D.gather_topk(n, docs, scs)      # NCCL over NVLink: the only collective of the path
 
     for _ in range(warmup):
         step_device()

@@ -54,6 +54,19 @@ struct DBuf {
     if (e == cudaSuccess) cap = c;
     return e;
   }
+  // grow, keeping the first `keep` elements (device-to-device copy on `st`)
+  cudaError_t ensure_keep(size_t n, size_t keep, cudaStream_t st) {
+    if (n <= cap && p) return cudaSuccess;
+    size_t c = n + n / 2 + 64;
+    T* np_ = nullptr;
+    cudaError_t e = cudaMalloc((void**)&np_, c * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpyAsync(np_, p, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (p) cudaFree(p);
+    p = np_; cap = c;
+    return e;
+  }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   ~DBuf() { release(); }
   DBuf() = default;
@@ -190,7 +203,9 @@ struct pb_batch {
   DBuf<uint64_t> term_byte_off, query_term_off;
   // plan
   DBuf<uint32_t> qt_lo, qt_hi, qt_len, qt_q;
-  DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_gsegoff, q_gtileoff;
+  DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_pbound, q_poff, q_gsegoff, q_gtileoff;
+  DBuf<uint8_t> q_scheme;
+  DBuf<ull> xcount;
   DBuf<ull> s_tiles, s_tile_off, g_tiles, g_tile_off;
   DBuf<Seg> seg_s, seg_g;
   DBuf<uint8_t> cub_temp;
@@ -211,7 +226,7 @@ struct pb_batch {
   uint32_t tab_tfcap[4] = {}, tab_flcap[4] = {}, tab_off[4] = {}, tab_total = 0;
   bool tab_full = false;
   // host staging
-  std::vector<ull> h_recoff, h_gidx, h_gsegoff, h_gtileoff;
+  std::vector<ull> h_recoff, h_poff, h_gidx, h_gsegoff, h_gtileoff;
   pb_batch_stats st{};
 
   ~pb_batch() {
@@ -322,7 +337,8 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   CU(b->qt_lo.ensure(NT + 1)); CU(b->qt_hi.ensure(NT + 1)); CU(b->qt_len.ensure(NT + 1)); CU(b->qt_q.ensure(NT + 1));
   CU(b->qt_gcount.ensure(NT + 2)); CU(b->qt_goff.ensure(NT + 2));
   CU(b->q_isg.ensure(Q + 2)); CU(b->q_gidx.ensure(Q + 2)); CU(b->q_grows.ensure(Q + 2)); CU(b->q_prim.ensure(Q + 2));
-  CU(b->q_recbound.ensure(Q + 2)); CU(b->q_recoff.ensure(Q + 2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
+  CU(b->q_recbound.ensure(Q + 2)); CU(b->q_recoff.ensure(Q + 2)); CU(b->q_pbound.ensure(Q + 2)); CU(b->q_poff.ensure(Q + 2));
+  CU(b->q_scheme.ensure(Q + 2)); CU(b->xcount.ensure(2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
   CU(b->s_tiles.ensure(Q + 2)); CU(b->s_tile_off.ensure(Q + 2));
   CU(b->seg_s.ensure(Q + 1));
   CU(b->n_results.ensure(Q + 1)); CU(b->doc_digest.ensure(Q + 1)); CU(b->score_digest.ensure(Q + 1));
@@ -419,7 +435,7 @@ int launch_fold(pb_batch* b, const FoldParams& FP) {
 }
 
 // Side-path capacity knobs (bytes of HBM the workspace may take).
-constexpr uint64_t REC_CAP_DEFAULT = 48ull << 20;       // records per round (x32 B with sort buffers)
+constexpr uint64_t REC_CAP_DEFAULT = 128ull << 20;      // records per round (x32 B with sort buffers)
 constexpr uint64_t REC_CAP_MAX = 1ull << 31;
 constexpr uint64_t BITMAP_POOL_BYTES = 6ull << 30;    // per-query doc bitmaps of one round
 
@@ -478,7 +494,8 @@ int batch_run(pb_batch* b) {
   std::vector<Round> rounds;
   const uint32_t doc_bits = bits_for(std::max<uint64_t>(ix->n_docs, 2));
   const uint32_t bitmap_sum_words = (uint32_t)(ix->n_docs / 32768 + 1);
-  const uint32_t bitmap_words = bitmap_sum_words + (uint32_t)((ix->n_docs + 31) / 32 + 1);
+  const uint32_t bitmap_doc_words = (uint32_t)((ix->n_docs + 31) / 32 + 1);
+  const uint32_t bitmap_words = bitmap_sum_words + 2 * bitmap_doc_words;
   uint64_t rec_cap = 0, slot_cap = 0;
   if (n_gsegs) {
     CU(b->seg_g.ensure(n_gsegs + 1));
@@ -489,17 +506,20 @@ int batch_run(pb_batch* b) {
                                                    b->q_prim.p, b->stats.p + ST_COUNT);
     CU(cudaGetLastError());
     gprimary_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q, b->q_isg.p, b->q_grows.p, b->q_prim.p, b->seg_g.p,
-                                                                     b->q_recbound.p, b->query_term_off.p, b->qt_goff.p,
-                                                                     b->q_gsegoff.p);
+                                                                     b->q_recbound.p, b->q_pbound.p, b->q_scheme.p,
+                                                                     b->query_term_off.p, b->qt_goff.p, b->q_gsegoff.p);
     CU(cudaGetLastError());
     RC(scan_ull(b, b->g_tiles.p, b->g_tile_off.p, n_gsegs + 1));
     RC(scan_ull(b, b->q_recbound.p, b->q_recoff.p, Q + 1));
+    RC(scan_ull(b, b->q_pbound.p, b->q_poff.p, Q + 1));
     RC(scan_ull(b, b->q_isg.p, b->q_gidx.p, Q + 1));
     gather_tileoff_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q + 1, b->q_gsegoff.p, b->g_tile_off.p, b->q_gtileoff.p);
     CU(cudaGetLastError());
-    launches += 6;
+    launches += 7;
+    b->h_poff.resize(Q + 1);
     b->h_recoff.resize(Q + 1); b->h_gidx.resize(Q + 1); b->h_gsegoff.resize(Q + 1); b->h_gtileoff.resize(Q + 1);
     CU(cudaMemcpyAsync(b->h_recoff.data(), b->q_recoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_poff.data(), b->q_poff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_gidx.data(), b->q_gidx.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_gsegoff.data(), b->q_gsegoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_gtileoff.data(), b->q_gtileoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -526,11 +546,13 @@ int batch_run(pb_batch* b) {
   // partial top-k lists: <= 2 per warp per launch + 2 per class-G query
   const uint64_t max_warps = (uint64_t)ix->sm_count * 8 * WARPS_PER_CTA;
   const uint64_t n_gq = n_gsegs ? b->h_gidx[Q] : 0;
-  const uint64_t part_cap = 2 * max_warps * (1 + 2 * rounds.size()) + 2 * n_gq + 64;
+  uint64_t part_cap = 2 * max_warps * (1 + 2 * rounds.size()) + 2 * n_gq + 64;
   if (part_cap >= 0xFFFFFFF0ull) { pb::set_error("too many partial lists"); return PB_ERR_UNSUPPORTED; }
+  const uint32_t kk = std::max<uint32_t>(k, 1);
   CU(b->part_next.ensure(part_cap)); CU(b->part_n.ensure(part_cap));
-  CU(b->part_doc.ensure(part_cap * std::max<uint32_t>(k, 1)));
-  CU(b->part_score.ensure(part_cap * std::max<uint32_t>(k, 1)));
+  CU(b->part_doc.ensure(part_cap * kk));
+  CU(b->part_score.ensure(part_cap * kk));
+  uint64_t part_bound = 2 * max_warps;      // host-side upper bound of the device's partial-list counter
 
   ScoreParams P;
   std::memset(&P, 0, sizeof(P));
@@ -551,7 +573,8 @@ int batch_run(pb_batch* b) {
   P.tab_full = b->tab_full ? 1u : 0u;
   P.boosts_all_one = 1u;
   for (uint32_t f = 0; f < ix->F; ++f) if (b->boost[f] != 1.0) P.boosts_all_one = 0u;
-  P.doc_bits = doc_bits; P.bitmap_words = bitmap_words; P.bitmap_sum_words = bitmap_sum_words;
+  P.doc_bits = doc_bits; P.bitmap_words = bitmap_words; P.bitmap_sum_words = bitmap_sum_words; P.bitmap_doc_words = bitmap_doc_words;
+  P.xcount = b->xcount.p;
   P.rec_count = b->counters.p + 1;
   CU(cudaEventRecord(b->ev[2], st));
 
@@ -582,16 +605,63 @@ int batch_run(pb_batch* b) {
     P.bitmap = b->bitmap.p;
     P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)rec_cap;
     P.stats = b->stats.p + ST_COUNT;
-    for (auto& r : rounds) {
+    // Rounds are planned with an ESTIMATE for exact-scheme queries; the marking pass counts the
+    // real number of diverted rows, and a round that would overflow the record buffers is split
+    // (its marks are cleared first) before anything has been scored.
+    auto make_round = [&](uint64_t qa, uint64_t qb) {
+      return Round{qa, qb, b->h_gsegoff[qa], b->h_gsegoff[qb], b->h_gtileoff[qa], b->h_gtileoff[qb],
+                   b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa]};
+    };
+    std::vector<Round> work(rounds.rbegin(), rounds.rend());
+    uint32_t n_rounds = 0;
+    while (!work.empty()) {
+      Round r = work.back();
+      work.pop_back();
+      if (r.sb == r.sa) continue;
       P.seg_begin = (uint32_t)r.sa; P.seg_end = (uint32_t)r.sb; P.tile_begin = r.ta; P.tile_end = r.tb;
       const uint64_t nseg = r.sb - r.sa, tiles = r.tb - r.ta;
-      gslot_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, (uint32_t)r.qa);
+      gslot_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, b->q_scheme.p, (uint32_t)r.qa);
       CU(cudaGetLastError());
       int mgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * 8, (tiles + 15) / 16));
+      CU(cudaMemsetAsync(b->xcount.p, 0, sizeof(ull), st));
       RC(launch_mark(b, P, mgrid, 0));
-      CU(cudaGetLastError());
+      launches += 2;
+      ull h_x = 0;
+      CU(cudaMemcpyAsync(&h_x, b->xcount.p, sizeof(ull), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      const uint64_t need = h_x + (b->h_poff[r.qb] - b->h_poff[r.qa]);
+      if (need > rec_cap) {
+        RC(launch_mark(b, P, mgrid, 1));      // undo the marks; nothing was scored yet
+        ++launches;
+        if (r.qb - r.qa > 1) {
+          uint64_t mid = r.qa + (r.qb - r.qa) / 2;
+          work.push_back(make_round(mid, r.qb));
+          work.push_back(make_round(r.qa, mid));
+          continue;
+        }
+        if (need > REC_CAP_MAX) { pb::set_error("a single query needs %llu side-path records (> %llu)", (ull)need, (ull)REC_CAP_MAX); return PB_ERR_UNSUPPORTED; }
+        rec_cap = need + 1024;
+        CU(b->rec_key.ensure(rec_cap)); CU(b->rec_val.ensure(rec_cap));
+        CU(b->rec_key2.ensure(rec_cap)); CU(b->rec_val2.ensure(rec_cap));
+        P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)rec_cap;
+        work.push_back(r);
+        continue;
+      }
+      ++n_rounds;
+      // partial top-k lists this round can add: <= 2 per warp per launch (score, fold) + 2 per query
+      part_bound += 4 * max_warps + 2 * r.slots;
+      if (part_bound > part_cap) {           // rounds were split: grow, keeping the lists written so far
+        const uint64_t ncap = part_bound * 2;
+        if (ncap >= 0xFFFFFFF0ull) { pb::set_error("too many partial lists"); return PB_ERR_UNSUPPORTED; }
+        CU(b->part_next.ensure_keep(ncap, part_cap, st)); CU(b->part_n.ensure_keep(ncap, part_cap, st));
+        CU(b->part_doc.ensure_keep(ncap * kk, part_cap * kk, st));
+        CU(b->part_score.ensure_keep(ncap * kk, part_cap * kk, st));
+        part_cap = ncap;
+        P.out.part_next = b->part_next.p; P.out.part_n = b->part_n.p; P.out.part_doc = b->part_doc.p;
+        P.out.part_score = b->part_score.p; P.out.part_cap = (uint32_t)part_cap;
+      }
       RC(launch_score(b, P, true, tiles));
-      launches += 3;
+      ++launches;
       uint32_t h_rec = 0;
       CU(cudaMemcpyAsync(&h_rec, b->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
@@ -611,10 +681,10 @@ int batch_run(pb_batch* b) {
         launches += 2 + (uint32_t)((end_bit + 7) / 8);
       }
       RC(launch_mark(b, P, mgrid, 1));
-      CU(cudaGetLastError());
       ++launches;
       CU(cudaMemsetAsync(b->counters.p + 1, 0, sizeof(uint32_t), st));
     }
+    S.side_rounds = n_rounds;
   }
   CU(cudaEventRecord(b->ev[4], st));
 

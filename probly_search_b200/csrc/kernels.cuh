@@ -32,7 +32,12 @@ constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 #define PB_SCORE_MIN_BLOCKS 3      // resident CTAs per SM the scoring kernel is compiled for (F <= 2)
 #endif
 
-enum SegMode : uint8_t { MODE_DIRECT = 0, MODE_PRIMARY = 1, MODE_SECONDARY = 2 };
+// How a posting list of a multi-list query is treated by the scoring kernel:
+//   PRIMARY / SECONDARY ("primary scheme", few secondary rows): the secondary lists mark their
+//     docs and are diverted whole; the primary (largest) list diverts only rows whose doc is marked.
+//   MULTI ("exact scheme", many secondary rows): a marking pass over ALL lists finds the docs hit
+//     by >= 2 (query term, expansion) events; every list diverts exactly those rows.
+enum SegMode : uint8_t { MODE_DIRECT = 0, MODE_PRIMARY = 1, MODE_SECONDARY = 2, MODE_MULTI = 3 };
 
 // One posting list walked for one (query term, expanded term): the unit query.rs:38-91 iterates.
 struct __align__(16) Seg {
@@ -128,6 +133,8 @@ struct ScoreParams {
   uint32_t* bitmap;              // [slots][bitmap_words]
   uint32_t bitmap_words;         // words per slot (summary + doc bits)
   uint32_t bitmap_sum_words;     // leading summary words of a slot
+  uint32_t bitmap_doc_words;     // words of one per-doc bit plane (a slot has two)
+  unsigned long long* xcount;    // exact-scheme rows the scoring pass will divert (counted while marking)
   unsigned long long* rec_key;
   unsigned long long* rec_val;
   uint32_t* rec_count;
@@ -525,7 +532,8 @@ __global__ void gfill_kernel(IndexView ix, uint64_t n_qterms, const uint64_t* __
 __global__ void gprimary_kernel(uint64_t n_queries, const unsigned long long* __restrict__ q_isg,
                                 const unsigned long long* __restrict__ q_grows,
                                 const unsigned long long* __restrict__ q_prim, Seg* __restrict__ seg_g,
-                                unsigned long long* __restrict__ q_recbound,
+                                unsigned long long* __restrict__ q_recbound, unsigned long long* __restrict__ q_pbound,
+                                uint8_t* __restrict__ q_scheme,
                                 const uint64_t* __restrict__ query_term_off,
                                 const unsigned long long* __restrict__ qt_goff,
                                 unsigned long long* __restrict__ q_gsegoff) {
@@ -533,23 +541,37 @@ __global__ void gprimary_kernel(uint64_t n_queries, const unsigned long long* __
   if (q > n_queries) return;
   q_gsegoff[q] = qt_goff[query_term_off[q]];   // qt_goff has n_qterms + 1 entries
   if (q == n_queries) return;
-  unsigned long long bound = 0;
+  unsigned long long bound = 0, pbound = 0;
+  uint8_t scheme = 0;
   if (q_isg[q]) {
     unsigned long long p = q_prim[q];
     uint32_t idx = 0xFFFFFFFFu - (uint32_t)(p & 0xFFFFFFFFull);
     unsigned long long prows = p >> 32;
-    seg_g[idx].mode = MODE_PRIMARY;
-    bound = 2ull * (q_grows[q] - prows);
+    unsigned long long rows = q_grows[q], secondary = rows - prows;
+    if (secondary * 16ull >= rows) {
+      // exact scheme: the record count is only known after the marking pass; plan with an estimate
+      scheme = 1;
+      bound = rows / 4 + 1024;
+    } else {
+      // primary scheme: every secondary row + at most one primary row per secondary doc
+      seg_g[idx].mode = MODE_PRIMARY;
+      bound = pbound = 2ull * secondary;
+    }
   }
   q_recbound[q] = bound;
+  q_pbound[q] = pbound;
+  q_scheme[q] = scheme;
 }
 
 // Assign bitmap slots for one round: slot = rank of the query among the round's class-G queries.
 __global__ void gslot_kernel(Seg* __restrict__ seg_g, uint64_t seg_begin, uint64_t seg_end,
-                             const unsigned long long* __restrict__ q_gidx, uint32_t q_begin) {
+                             const unsigned long long* __restrict__ q_gidx, const uint8_t* __restrict__ q_scheme,
+                             uint32_t q_begin) {
   uint64_t i = seg_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= seg_end) return;
-  seg_g[i].slot = (uint32_t)(q_gidx[seg_g[i].q] - q_gidx[q_begin]);
+  const uint32_t q = seg_g[i].q;
+  seg_g[i].slot = (uint32_t)(q_gidx[q] - q_gidx[q_begin]);
+  if (q_scheme[q]) seg_g[i].mode = MODE_MULTI;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -565,7 +587,11 @@ __device__ __forceinline__ uint32_t seg_of_tile(const uint64_t* __restrict__ til
   return a;
 }
 
-// mark (or clear) the docs of SECONDARY segments in the query's bitmap
+// Marking pass of a side-path round (clear = 1 undoes it afterwards).  Slot layout of a query:
+//   [summary: 1 bit per 1024 docs][bits A: 1 bit per doc][bits B: 1 bit per doc]
+// primary scheme: SECONDARY lists set A (= "diverted docs") and the summary.
+// exact scheme:   every list sets A (= "seen"); a doc seen again sets B (= "multi") and the
+//                 summary, and the exact number of rows the scoring pass will divert is counted.
 template <int F>
 __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant__ ScoreParams P, int clear) {
   const int lane = threadIdx.x & 31;
@@ -576,14 +602,16 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
   const uint64_t t1 = P.tile_begin + (T * (w + 1)) / W;
   if (t >= t1) return;
   uint32_t s = seg_of_tile(P.tile_off, P.seg_begin, P.seg_end, t);
+  unsigned long long xcount = 0;
   while (t < t1) {
     const Seg sg = P.segs[s];
     const uint64_t st0 = P.tile_off[s], st1 = P.tile_off[s + 1];
     const uint64_t tend = min(t1, st1);
-    if (sg.mode == MODE_SECONDARY) {
-      // slot layout: [summary words: 1 bit per 1024 docs][doc words: 1 bit per doc]
+    if (sg.mode == MODE_SECONDARY || sg.mode == MODE_MULTI) {
       uint32_t* sm = P.bitmap + (size_t)sg.slot * P.bitmap_words;
-      uint32_t* bm = sm + P.bitmap_sum_words;
+      uint32_t* ba = sm + P.bitmap_sum_words;
+      uint32_t* bb = ba + P.bitmap_doc_words;
+      const bool exact = sg.mode == MODE_MULTI;
       const uint64_t abs0 = sg.row_begin / TILE_ROWS;
       const uint64_t rend = sg.row_begin + sg.n_rows;
       for (; t < tend; ++t) {
@@ -594,10 +622,19 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
         for (int j = 0; j < 4; ++j) {
           uint64_t row = row0 + j;
           if (row >= sg.row_begin && row < rend) {
-            if (clear) { bm[dv[j] >> 5] = 0u; sm[dv[j] >> 15] = 0u; }
-            else {
-              atomicOr(&bm[dv[j] >> 5], 1u << (dv[j] & 31));
-              atomicOr(&sm[dv[j] >> 15], 1u << ((dv[j] >> 10) & 31));
+            const uint32_t doc = dv[j], bit = 1u << (doc & 31);
+            if (clear) {
+              ba[doc >> 5] = 0u; sm[doc >> 15] = 0u;
+              if (exact) bb[doc >> 5] = 0u;
+            } else if (!exact) {
+              atomicOr(&ba[doc >> 5], bit);
+              atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
+            } else {
+              if (atomicOr(&ba[doc >> 5], bit) & bit) {          // seen before: a multi-event doc
+                const uint32_t old = atomicOr(&bb[doc >> 5], bit);
+                atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
+                xcount += (old & bit) ? 1u : 2u;                  // this row (+ the doc's first row)
+              }
             }
           }
         }
@@ -606,6 +643,8 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
     t = tend;
     ++s;
   }
+  xcount = warp_sum_u64(xcount);
+  if (lane == 0 && xcount) atomicAdd(P.xcount, xcount);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -962,7 +1001,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? PB_SCORE_MIN_BLOCKS : 2
       }
       if (GMODE) {
         C.sum = P.bitmap + (size_t)sg.slot * P.bitmap_words;
-        C.bm = C.sum + P.bitmap_sum_words;
+        C.bm = C.sum + P.bitmap_sum_words + (sg.mode == MODE_MULTI ? P.bitmap_doc_words : 0u);
       }
       const uint64_t abs0 = C.rbeg / TILE_ROWS;
 #if PB_TMA
