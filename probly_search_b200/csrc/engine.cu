@@ -680,8 +680,13 @@ int batch_run(pb_batch* b) {
         RC(launch_fold(b, FP));
         launches += 2 + (uint32_t)((end_bit + 7) / 8);
       }
-      RC(launch_mark(b, P, mgrid, 1));
-      ++launches;
+      // undo the marks: re-walk the marked rows, or wipe the round's slots when that is less traffic
+      if ((uint64_t)tiles * TILE_ROWS * 4 > r.slots * (uint64_t)bitmap_words * 4) {
+        CU(cudaMemsetAsync(b->bitmap.p, 0, r.slots * (size_t)bitmap_words * sizeof(uint32_t), st));
+      } else {
+        RC(launch_mark(b, P, mgrid, 1));
+        ++launches;
+      }
       CU(cudaMemsetAsync(b->counters.p + 1, 0, sizeof(uint32_t), st));
     }
     S.side_rounds = n_rounds;

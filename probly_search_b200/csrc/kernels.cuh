@@ -551,7 +551,7 @@ __global__ void gprimary_kernel(uint64_t n_queries, const unsigned long long* __
     if (secondary * 16ull >= rows) {
       // exact scheme: the record count is only known after the marking pass; plan with an estimate
       scheme = 1;
-      bound = rows / 4 + 1024;
+      bound = rows / 2 + 1024;
     } else {
       // primary scheme: every secondary row + at most one primary row per secondary doc
       seg_g[idx].mode = MODE_PRIMARY;
@@ -1113,98 +1113,248 @@ __device__ __forceinline__ bool next_event(const unsigned long long* val, uint32
   return found;
 }
 
+// Slow per-thread fold of ONE doc's events [i, e) straight from global memory: used only for docs
+// with more than 32 events (they do not fit a warp window).  Same rules as the warp path below.
+template <int F, int SCORER>
+__device__ __noinline__ bool fold_group_slow(const FoldParams& FP, uint32_t i, uint32_t e, uint32_t q, double* out) {
+  const ScoreParams& P = FP.S;
+  bool has = false;
+  double result = 0.0;
+  if (SCORER == 0) {
+    uint32_t cur = NONE;
+    unsigned long long last = 0, v;
+    bool first_ev = true;
+    while (next_event(FP.val, i, e, first_ev, last, &v)) {
+      first_ev = false; last = v;
+      const Seg sg = P.segs[(uint32_t)(v >> 32)];
+      bool firstq = (sg.qti != cur);
+      cur = sg.qti;
+      double sc = bm25_row_score<F>(P, sg, (uint32_t)v);
+      if (!(sc > 0.0)) continue;
+      if (!has) { result = sc; has = true; }
+      else if (firstq) result = __dadd_rn(result, sc);
+      else result = fmax(result, sc);
+    }
+  } else {
+    has = true;
+    const uint32_t qtl = (uint32_t)(P.query_term_off[q + 1] - P.query_term_off[q]);
+    const uint32_t ne = e - i;
+#pragma unroll 1
+    for (int x = 0; x < F; ++x) {
+      double accx = 0.0;
+      unsigned long long done_lo = 0, acc_lo = 0;
+      for (uint32_t step = 0; step < ne; ++step) {
+        int bj = -1; double bs = 0.0; unsigned long long bv = 0; uint32_t btf = 0, bfl = 0, bterm = 0, bqti = 0;
+        for (uint32_t j = 0; j < ne && j < 64; ++j) {
+          if ((done_lo >> j) & 1ull) continue;
+          unsigned long long v = FP.val[i + j];
+          uint32_t row = (uint32_t)v;
+          uint32_t tf = row_tf<F>(P.ix.post_blocks, row, x);
+          if (tf == 0) { done_lo |= 1ull << j; continue; }
+          const Seg sg = P.segs[(uint32_t)(v >> 32)];
+          double sc = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
+          if (bj < 0 || sc > bs || (sc == bs && v < bv)) {
+            bj = (int)j; bs = sc; bv = v; btf = tf; bfl = row_fl<F>(P.ix.post_blocks, row, x); bterm = sg.term; bqti = sg.qti;
+          }
+        }
+        if (bj < 0) break;
+        done_lo |= 1ull << bj;
+        bool consumed = false; uint32_t used = 0;
+        for (uint32_t j = 0; j < ne && j < 64; ++j) {
+          if (!((acc_lo >> j) & 1ull)) continue;
+          const Seg sg = P.segs[(uint32_t)(FP.val[i + j] >> 32)];
+          consumed |= (sg.qti == bqti);
+          used += (sg.term == bterm);
+        }
+        if (consumed || used >= btf) continue;
+        acc_lo |= 1ull << bj;
+        accx = __dadd_rn(accx, z2o_entry(bs, btf, bfl, qtl));
+      }
+      result = fmax(accx, result);
+    }
+    if (ne > 64) atomicOr(P.out.error_flag, 4u);   // > 64 events on one doc: outside the envelope
+  }
+  *out = result;
+  return has;
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+  return __longlong_as_double((long long)shfl_u64((uint64_t)__double_as_longlong(v), src));
+}
+
+// Warp-cooperative fold.  A warp walks its span of the sorted records in windows of 32: lane =
+// record.  Every lane gathers its own event (segment descriptor, posting row) — 32 independent
+// gathers in flight — then the events of a doc (consecutive lanes) are put in processing order
+// with a few shuffles and combined:
+//   BM25     order = segment index = (query term, expansion rank): has/first/max fold of
+//            query.rs:150-164, None events still marking the doc visited.
+//   ZeroToOne order = (entry score desc, event order asc) = the stable sort of zero_to_one.rs:98;
+//            one candidate per doc per step; the lanes holding accepted entries vote whether the
+//            candidate's query term is consumed / its term's pool exhausted (zero_to_one.rs:101-115).
+// A window always starts at a doc boundary; a doc cut by the window end is deferred to the next
+// window; docs with more than 32 events take fold_group_slow.
 template <int F, int SCORER>
 __global__ void __launch_bounds__(CTA_THREADS) fold_kernel(const __grid_constant__ FoldParams FP) {
   const ScoreParams& P = FP.S;
   const int lane = threadIdx.x & 31;
   const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint64_t n32 = (FP.n + 31) / 32;
-  const uint64_t g0 = (n32 * w) / W, g1 = (n32 * (w + 1)) / W;
+  const uint32_t n = FP.n;
+  uint32_t base = (uint32_t)(((uint64_t)n * w) / W);
+  const uint32_t stop = (uint32_t)(((uint64_t)n * (w + 1)) / W);     // docs whose head is < stop are ours
+  // move to the first doc boundary at or after `base`
+  while (base > 0 && base < n && FP.key[base] == FP.key[base - 1]) ++base;
   WarpAcc acc;
   acc.reset(NONE);
-  for (uint64_t g = g0; g < g1; ++g) {
-    const uint32_t i = (uint32_t)(g * 32 + lane);
-    bool head = false;
-    unsigned long long key = 0;
-    if (i < FP.n) {
-      key = FP.key[i];
-      head = (i == 0) || (FP.key[i - 1] != key);
+  const uint64_t doc_mask = (1ull << P.doc_bits) - 1ull;
+
+  while (base < stop) {
+    const uint32_t i = base + lane;
+    const uint32_t n_in = min(32u, n - base);
+    bool in = lane < (int)n_in;
+    unsigned long long key = in ? FP.key[i] : ~0ull;
+    const unsigned long long key_up = __shfl_up_sync(0xffffffffu, key, 1);
+    bool head = in && (lane == 0 || key_up != key);
+    uint32_t hm = __ballot_sync(0xffffffffu, head);
+    // `lim` = first lane that is NOT processed in this window:
+    //  - docs whose head is at or after `stop` belong to the next warp;
+    //  - a doc cut by the window end is deferred to the next window (or, if it fills the whole
+    //    window, i.e. has more than 32 events, folded by the slow path right here).
+    uint32_t lim = 32;
+    if (stop - base < 32u) {
+      const uint32_t hb = hm & (0xFFFFFFFFu << (stop - base));
+      if (hb) lim = (uint32_t)(__ffs(hb) - 1);
     }
-    bool has = false;
-    double result = 0.0;
-    uint32_t doc = 0, q = NONE;
-    if (head) {
-      uint32_t e = i + 1;
-      while (e < FP.n && FP.key[e] == key) ++e;
-      doc = (uint32_t)(key & ((1ull << P.doc_bits) - 1ull));
-      q = P.segs[(uint32_t)(FP.val[i] >> 32)].q;
-      if (SCORER == 0) {
-        // max_score_merger, query.rs:150-164, as the per-doc fold of SURVEY Appendix B
-        uint32_t cur = NONE;
-        unsigned long long last = 0, v;
-        bool first_ev = true;
-        while (next_event(FP.val, i, e, first_ev, last, &v)) {
-          first_ev = false; last = v;
-          const Seg sg = P.segs[(uint32_t)(v >> 32)];
-          bool firstq = (sg.qti != cur);
-          cur = sg.qti;
-          double sc = bm25_row_score<F>(P, sg, (uint32_t)v);
-          if (!(sc > 0.0)) continue;                 // None: the doc is still marked visited
-          if (!has) { result = sc; has = true; }
-          else if (firstq) result = __dadd_rn(result, sc);
-          else result = fmax(result, sc);
+    if (lim == 32 && n_in == 32 && base + 32 < n) {
+      const unsigned long long knext = FP.key[base + 32];
+      if (__shfl_sync(0xffffffffu, key, 31) == knext) {
+        const int h31 = 31 - __clz(hm);               // head lane of the cut doc
+        if (h31 == 0) {
+          uint32_t e = base + 32;
+          while (e < n && FP.key[e] == key) ++e;       // every lane holds the same key here
+          double r = 0.0;
+          bool hs = false;
+          const uint32_t q0 = P.segs[(uint32_t)(FP.val[base] >> 32)].q;
+          if (lane == 0) hs = fold_group_slow<F, SCORER>(FP, base, e, q0, &r);
+          if (acc.q != q0) { if (acc.q != NONE) acc.flush(P.out, false, lane); acc.reset(q0); }
+          acc.add(P.out, lane == 0 && hs, (uint32_t)(key & doc_mask), r, lane);
+          base = e;
+          continue;
         }
-      } else {
-        // ZeroToOne::finalize, zero_to_one.rs:84-126.  Entries of field x = events with
-        // tf[x] > 0, visited by (score desc, event order asc) = a stable sort by score;
-        // accept iff the query term is not consumed and the term's pool is not exhausted
-        // (accepted so far with this term < tf[x]).
-        has = true;
-        const uint32_t qtl = (uint32_t)(P.query_term_off[q + 1] - P.query_term_off[q]);
-        const uint32_t ne = e - i;
-#pragma unroll 1
-        for (int x = 0; x < F; ++x) {
-          double accx = 0.0;
-          // "processed" / "accepted" flags per event: bit masks over the (unsorted) positions
-          unsigned long long done_lo = 0, acc_lo = 0;
-          for (uint32_t step = 0; step < ne; ++step) {
-            // pick the unprocessed entry with max score, ties by smaller val
-            int bj = -1; double bs = 0.0; unsigned long long bv = 0; uint32_t btf = 0, bfl = 0, bterm = 0, bqti = 0;
-            for (uint32_t j = 0; j < ne && j < 64; ++j) {
-              if ((done_lo >> j) & 1ull) continue;
-              unsigned long long v = FP.val[i + j];
-              uint32_t row = (uint32_t)v;
-              uint32_t tf = row_tf<F>(P.ix.post_blocks, row, x);
-              if (tf == 0) { done_lo |= 1ull << j; continue; }
-              const Seg sg = P.segs[(uint32_t)(v >> 32)];
-              double sc = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
-              if (bj < 0 || sc > bs || (sc == bs && v < bv)) {
-                bj = (int)j; bs = sc; bv = v; btf = tf; bfl = row_fl<F>(P.ix.post_blocks, row, x); bterm = sg.term; bqti = sg.qti;
-              }
-            }
-            if (bj < 0) break;
-            done_lo |= 1ull << bj;
-            bool consumed = false; uint32_t used = 0;
-            for (uint32_t j = 0; j < ne && j < 64; ++j) {
-              if (!((acc_lo >> j) & 1ull)) continue;
-              const Seg sg = P.segs[(uint32_t)(FP.val[i + j] >> 32)];
-              consumed |= (sg.qti == bqti);
-              used += (sg.term == bterm);
-            }
-            if (consumed || used >= btf) continue;
-            acc_lo |= 1ull << bj;
-            accx = __dadd_rn(accx, z2o_entry(bs, btf, bfl, qtl));
-          }
-          result = fmax(accx, result);
-        }
-        if (ne > 64) atomicOr(P.out.error_flag, 4u);   // > 64 events on one doc: outside the envelope
+        lim = (uint32_t)h31;
       }
     }
+    if (lim < 32) {
+      in = in && lane < (int)lim;
+      head = head && lane < (int)lim;
+      hm &= (1u << lim) - 1u;
+    }
+    const uint32_t advance = min(lim, n_in);
+    // group geometry
+    const int my_head = 31 - __clz(hm & (0xFFFFFFFFu >> (31 - lane)));
+    const uint32_t above = hm & (0xFFFFFFFEu << my_head);
+    const int g_end = above ? (__ffs(above) - 1) : (int)advance;
+    const int size = in ? g_end - my_head : 0;
+    const int pos = lane - my_head;
+    const uint32_t gmask = in ? (((size >= 32) ? 0xFFFFFFFFu : ((1u << size) - 1u)) << my_head) : 0u;
+    int maxsize = size;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxsize = max(maxsize, __shfl_xor_sync(0xffffffffu, maxsize, o));
+
+    // every lane gathers its own event
+    unsigned long long val = in ? FP.val[i] : 0ull;
+    Seg sg;
+    sg.q = NONE; sg.qti = 0; sg.term = 0; sg.qlen = 0;
+    if (in) sg = P.segs[(uint32_t)(val >> 32)];
+    const uint32_t row = (uint32_t)val;
+    const uint32_t doc = (uint32_t)(key & doc_mask);
+    uint32_t q = sg.q;
+    double ev_score = 0.0;      // BM25: the event's score; ZeroToOne: the entry score of the term
+    uint32_t tfv[F], flv[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) { tfv[f] = 0; flv[f] = 0; }
+    if (in) {
+      if (SCORER == 0) {
+        ev_score = bm25_row_score<F>(P, sg, row);
+      } else {
+        ev_score = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
+#pragma unroll
+        for (int f = 0; f < F; ++f) { tfv[f] = row_tf<F>(P.ix.post_blocks, row, f); flv[f] = row_fl<F>(P.ix.post_blocks, row, f); }
+      }
+    }
+    // rank of the event inside its doc in processing order
+    int rank = 0;
+    for (int m = 0; m < maxsize; ++m) {
+      const int src = min(my_head + m, 31);
+      const unsigned long long ov = shfl_u64(val, src);
+      bool before;
+      if (SCORER == 0) {
+        before = ov < val;
+      } else {
+        const double os = shfl_f64(ev_score, src);
+        before = os > ev_score || (os == ev_score && ov < val);
+      }
+      if (m < size && m != pos && before) ++rank;
+    }
+    // pull the event that belongs at this lane's position
+    int src = lane;
+    for (int m = 0; m < maxsize; ++m) {
+      const int c = min(my_head + m, 31);
+      const int rc = __shfl_sync(0xffffffffu, rank, c);
+      if (m < size && rc == pos) src = c;
+    }
+    ev_score = shfl_f64(ev_score, src);
+    uint32_t e_qti = __shfl_sync(0xffffffffu, (uint32_t)sg.qti, src);
+    uint32_t e_term = __shfl_sync(0xffffffffu, sg.term, src);
+#pragma unroll
+    for (int f = 0; f < F; ++f) { tfv[f] = __shfl_sync(0xffffffffu, tfv[f], src); flv[f] = __shfl_sync(0xffffffffu, flv[f], src); }
+
+    bool has = false;
+    double result = 0.0;
+    if (SCORER == 0) {
+      uint32_t cur = NONE;
+      for (int m = 0; m < maxsize; ++m) {
+        const int c = min(my_head + m, 31);
+        const double sm = shfl_f64(ev_score, c);
+        const uint32_t qm = __shfl_sync(0xffffffffu, e_qti, c);
+        if (m < size) {
+          const bool firstq = qm != cur;
+          cur = qm;
+          if (sm > 0.0) {                          // None otherwise: the doc is only marked visited
+            if (!has) { result = sm; has = true; }
+            else if (firstq) result = __dadd_rn(result, sm);
+            else result = fmax(result, sm);
+          }
+        }
+      }
+    } else {
+      has = in;
+      const uint32_t qtl = in ? (uint32_t)(P.query_term_off[q + 1] - P.query_term_off[q]) : 0u;
+#pragma unroll
+      for (int x = 0; x < F; ++x) {
+        double accx = 0.0;
+        bool accepted = false;                     // this lane's entry was accepted for field x
+        for (int m = 0; m < maxsize; ++m) {
+          const int c = min(my_head + m, 31);
+          const uint32_t c_qti = __shfl_sync(0xffffffffu, e_qti, c);
+          const uint32_t c_term = __shfl_sync(0xffffffffu, e_term, c);
+          const uint32_t c_tf = __shfl_sync(0xffffffffu, tfv[x], c);
+          const uint32_t conflict = __ballot_sync(0xffffffffu, accepted && e_qti == c_qti) & gmask;
+          const uint32_t used = __popc(__ballot_sync(0xffffffffu, accepted && e_term == c_term) & gmask);
+          const bool ok = m < size && c_tf > 0 && conflict == 0u && used < c_tf;
+          double contrib = 0.0;
+          if (ok && pos == m) { accepted = true; contrib = z2o_entry(ev_score, tfv[x], flv[x], qtl); }
+          contrib = shfl_f64(contrib, c);
+          if (ok) accx = __dadd_rn(accx, contrib);
+        }
+        result = fmax(accx, result);
+      }
+    }
+    has = has && head;
     // emit: lanes may belong to different queries (sorted, so at most a few switches)
-    uint32_t m = __ballot_sync(0xffffffffu, has);
-    while (m) {
-      int l = __ffs(m) - 1;
+    uint32_t mres = __ballot_sync(0xffffffffu, has);
+    while (mres) {
+      int l = __ffs(mres) - 1;
       uint32_t ql = __shfl_sync(0xffffffffu, q, l);
       bool mine = has && q == ql;
       if (acc.q != ql) {
@@ -1212,8 +1362,9 @@ __global__ void __launch_bounds__(CTA_THREADS) fold_kernel(const __grid_constant
         acc.reset(ql);
       }
       acc.add(P.out, mine, doc, result, lane);
-      m &= ~__ballot_sync(0xffffffffu, mine);
+      mres &= ~__ballot_sync(0xffffffffu, mine);
     }
+    base += advance;
   }
   if (acc.q != NONE) acc.flush(P.out, false, lane);
 }

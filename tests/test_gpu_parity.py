@@ -161,6 +161,20 @@ def test_full_results_sample_matches_oracle():
         H.assert_same_results([(int(d), float(s)) for d, s in zip(docs[sel], scores[sel])], exp, ctx=f"q={q}")
 
 
+def test_docs_with_many_events():
+    """A doc hit by more events than a warp window holds (> 32) takes the slow fold path."""
+    docs = [(0, [["abc xyz b"], ["abc abc b"]]), (1, [["xyz"], ["abc b"]]), (2, [["zz"], ["b"]])]
+    ix, o = both(docs, 2)
+    # "abc", "xyz", "b", "zz" expand only to themselves here: events per doc = matching query terms
+    queries = [" ".join(["abc"] * 40), " ".join(["abc", "b"] * 18), " ".join(["abc"] * 33 + ["b"] * 5 + ["xyz"] * 7)]
+    compare_queries(ix, o, queries, [1.0, 1.0], "many-events")
+    compare_queries(ix, o, queries, [0.5, -1.0], "many-events boosts")
+    from probly_search_b200 import capi
+    with pytest.raises(capi.ProblyError) as e:       # ZeroToOne envelope: <= 64 events per doc
+        ix.query_batch_flat(FlatQueries.from_strings([" ".join(["abc"] * 70)], TOK), score.zero_to_one.new(), [1.0, 1.0], top_k=1)
+    assert e.value.code == capi.PB_ERR_UNSUPPORTED
+
+
 def test_empty_and_degenerate_batches():
     ix, o = both([(0, [["a b"], ["c"]]), (1, [["b"], [""]])], 2)
     fq = FlatQueries.from_strings([], TOK)
