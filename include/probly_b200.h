@@ -208,7 +208,8 @@ typedef struct pb_batch_stats {
   uint64_t rows_streamed_direct; /* ... of which by the single launch over all single-list queries */
   uint64_t rows_scored;       /* rows whose doc is live = ScoreCalculator::score evaluations on
                                  de-duplicated rows ("scored postings") */
-  uint64_t rows_diverted;     /* rows routed through the sort+fold side path */
+  uint64_t rows_diverted;     /* rows routed through the per-doc fold side path */
+  uint64_t legacy_records;    /* ... of which through the sorted fallback (overflowing bins) */
   uint64_t results_emitted;   /* sum of n_results */
   uint64_t pointer_visits;    /* reference-equivalent DocumentPointer visits (sum of multiplicities) */
   uint32_t gpu_launches;      /* kernels launched by the last pb_batch_run */

@@ -69,7 +69,7 @@ class QueryResults(C.Structure):
 class BatchStats(C.Structure):
     _fields_ = [("n_queries", C.c_uint64), ("n_query_terms", C.c_uint64), ("n_segments", C.c_uint64),
                 ("rows_streamed", C.c_uint64), ("rows_streamed_direct", C.c_uint64),
-                ("rows_scored", C.c_uint64), ("rows_diverted", C.c_uint64),
+                ("rows_scored", C.c_uint64), ("rows_diverted", C.c_uint64), ("legacy_records", C.c_uint64),
                 ("results_emitted", C.c_uint64), ("pointer_visits", C.c_uint64), ("gpu_launches", C.c_uint32),
                 ("side_rounds", C.c_uint32), ("ms_total", C.c_float), ("ms_descend", C.c_float),
                 ("ms_plan", C.c_float), ("ms_score", C.c_float), ("ms_side", C.c_float),

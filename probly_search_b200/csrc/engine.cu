@@ -203,9 +203,11 @@ struct pb_batch {
   DBuf<uint64_t> term_byte_off, query_term_off;
   // plan
   DBuf<uint32_t> qt_lo, qt_hi, qt_len, qt_q;
-  DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_pbound, q_poff, q_gsegoff, q_gtileoff;
-  DBuf<uint8_t> q_scheme;
+  DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_nbins, q_binoff, q_gsegoff, q_gtileoff;
+  DBuf<uint8_t> q_scheme, q_shift;
   DBuf<ull> xcount;
+  DBuf<uint32_t> bin_count, bin_off, bin_cursor;
+  DBuf<uint4> rec;
   DBuf<ull> s_tiles, s_tile_off, g_tiles, g_tile_off;
   DBuf<Seg> seg_s, seg_g;
   DBuf<uint8_t> cub_temp;
@@ -226,7 +228,7 @@ struct pb_batch {
   uint32_t tab_tfcap[4] = {}, tab_flcap[4] = {}, tab_off[4] = {}, tab_total = 0;
   bool tab_full = false;
   // host staging
-  std::vector<ull> h_recoff, h_poff, h_gidx, h_gsegoff, h_gtileoff;
+  std::vector<ull> h_recoff, h_binoff, h_gidx, h_gsegoff, h_gtileoff;
   pb_batch_stats st{};
 
   ~pb_batch() {
@@ -239,6 +241,26 @@ struct pb_batch {
 namespace {
 
 int scan_ull(pb_batch* b, const ull* in, ull* out, size_t n_plus_1) {
+  size_t bytes = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n_plus_1, b->stream));
+  CU(b->cub_temp.ensure(bytes));
+  bytes = b->cub_temp.cap;
+  CU(cub::DeviceScan::ExclusiveSum(b->cub_temp.p, bytes, in, out, (int64_t)n_plus_1, b->stream));
+  return PB_OK;
+}
+
+__global__ void overflow_count_kernel(const uint32_t* __restrict__ bin_cursor, uint32_t n_bins, uint32_t* __restrict__ out) {
+  uint32_t s = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_bins; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t c = bin_cursor[i];
+    if (c > PB_WINDOW_MAX) s += c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+int scan_u32(pb_batch* b, const uint32_t* in, uint32_t* out, size_t n_plus_1) {
   size_t bytes = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n_plus_1, b->stream));
   CU(b->cub_temp.ensure(bytes));
@@ -337,8 +359,8 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   CU(b->qt_lo.ensure(NT + 1)); CU(b->qt_hi.ensure(NT + 1)); CU(b->qt_len.ensure(NT + 1)); CU(b->qt_q.ensure(NT + 1));
   CU(b->qt_gcount.ensure(NT + 2)); CU(b->qt_goff.ensure(NT + 2));
   CU(b->q_isg.ensure(Q + 2)); CU(b->q_gidx.ensure(Q + 2)); CU(b->q_grows.ensure(Q + 2)); CU(b->q_prim.ensure(Q + 2));
-  CU(b->q_recbound.ensure(Q + 2)); CU(b->q_recoff.ensure(Q + 2)); CU(b->q_pbound.ensure(Q + 2)); CU(b->q_poff.ensure(Q + 2));
-  CU(b->q_scheme.ensure(Q + 2)); CU(b->xcount.ensure(2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
+  CU(b->q_recbound.ensure(Q + 2)); CU(b->q_recoff.ensure(Q + 2)); CU(b->q_nbins.ensure(Q + 2)); CU(b->q_binoff.ensure(Q + 2));
+  CU(b->q_scheme.ensure(Q + 2)); CU(b->q_shift.ensure(Q + 2)); CU(b->xcount.ensure(2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
   CU(b->s_tiles.ensure(Q + 2)); CU(b->s_tile_off.ensure(Q + 2));
   CU(b->seg_s.ensure(Q + 1));
   CU(b->n_results.ensure(Q + 1)); CU(b->doc_digest.ensure(Q + 1)); CU(b->score_digest.ensure(Q + 1));
@@ -434,9 +456,24 @@ int launch_fold(pb_batch* b, const FoldParams& FP) {
   });
 }
 
+template <int F, int SC>
+int launch_binfold_t(pb_batch* b, const ScoreParams& P, int grid) {
+  binfold_kernel<F, SC><<<grid, CTA_THREADS, 0, b->stream>>>(P);
+  CU(cudaGetLastError());
+  return PB_OK;
+}
+int launch_binfold(pb_batch* b, const ScoreParams& P, uint64_t n_bins) {
+  uint64_t want = (n_bins + WARPS_PER_CTA * 4 - 1) / (WARPS_PER_CTA * 4);
+  int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)b->ix->sm_count * 6, want));
+  return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
+    return launch_binfold_t<decltype(f)::value, decltype(sc)::value>(b, P, grid);
+  });
+}
+
 // Side-path capacity knobs (bytes of HBM the workspace may take).
 constexpr uint64_t REC_CAP_DEFAULT = 128ull << 20;      // records per round (x32 B with sort buffers)
 constexpr uint64_t REC_CAP_MAX = 1ull << 31;
+constexpr uint64_t BIN_CAP = 96ull << 20;               // doc-range bins per round (12 B each)
 constexpr uint64_t BITMAP_POOL_BYTES = 6ull << 30;    // per-query doc bitmaps of one round
 
 int batch_run(pb_batch* b) {
@@ -505,21 +542,22 @@ int batch_run(pb_batch* b) {
                                                    b->qt_q.p, b->qt_gcount.p, b->qt_goff.p, b->seg_g.p, b->g_tiles.p,
                                                    b->q_prim.p, b->stats.p + ST_COUNT);
     CU(cudaGetLastError());
-    gprimary_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q, b->q_isg.p, b->q_grows.p, b->q_prim.p, b->seg_g.p,
-                                                                     b->q_recbound.p, b->q_pbound.p, b->q_scheme.p,
-                                                                     b->query_term_off.p, b->qt_goff.p, b->q_gsegoff.p);
+    gprimary_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q, doc_bits, b->q_isg.p, b->q_grows.p, b->q_prim.p,
+                                                                     b->seg_g.p, b->q_recbound.p, b->q_nbins.p, b->q_scheme.p,
+                                                                     b->q_shift.p, b->query_term_off.p, b->qt_goff.p,
+                                                                     b->q_gsegoff.p);
     CU(cudaGetLastError());
     RC(scan_ull(b, b->g_tiles.p, b->g_tile_off.p, n_gsegs + 1));
     RC(scan_ull(b, b->q_recbound.p, b->q_recoff.p, Q + 1));
-    RC(scan_ull(b, b->q_pbound.p, b->q_poff.p, Q + 1));
+    RC(scan_ull(b, b->q_nbins.p, b->q_binoff.p, Q + 1));
     RC(scan_ull(b, b->q_isg.p, b->q_gidx.p, Q + 1));
     gather_tileoff_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q + 1, b->q_gsegoff.p, b->g_tile_off.p, b->q_gtileoff.p);
     CU(cudaGetLastError());
     launches += 7;
-    b->h_poff.resize(Q + 1);
+    b->h_binoff.resize(Q + 1);
     b->h_recoff.resize(Q + 1); b->h_gidx.resize(Q + 1); b->h_gsegoff.resize(Q + 1); b->h_gtileoff.resize(Q + 1);
     CU(cudaMemcpyAsync(b->h_recoff.data(), b->q_recoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(b->h_poff.data(), b->q_poff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_binoff.data(), b->q_binoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_gidx.data(), b->q_gidx.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_gsegoff.data(), b->q_gsegoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_gtileoff.data(), b->q_gtileoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -534,7 +572,8 @@ int batch_run(pb_batch* b) {
       // largest qb with recoff[qb]-recoff[qa] <= rec_cap and gidx[qb]-gidx[qa] <= slot_cap
       uint64_t qb1 = std::upper_bound(b->h_recoff.begin() + qa, b->h_recoff.end(), b->h_recoff[qa] + rec_cap) - b->h_recoff.begin() - 1;
       uint64_t qb2 = std::upper_bound(b->h_gidx.begin() + qa, b->h_gidx.end(), b->h_gidx[qa] + slot_cap) - b->h_gidx.begin() - 1;
-      uint64_t qb = std::max<uint64_t>(qa + 1, std::min(qb1, qb2));
+      uint64_t qb3 = std::upper_bound(b->h_binoff.begin() + qa, b->h_binoff.end(), b->h_binoff[qa] + BIN_CAP) - b->h_binoff.begin() - 1;
+      uint64_t qb = std::max<uint64_t>(qa + 1, std::min(qb1, std::min(qb2, qb3)));
       Round r{qa, qb, b->h_gsegoff[qa], b->h_gsegoff[qb], b->h_gtileoff[qa], b->h_gtileoff[qb],
               b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa]};
       if (r.sb > r.sa) rounds.push_back(r);
@@ -575,6 +614,7 @@ int batch_run(pb_batch* b) {
   for (uint32_t f = 0; f < ix->F; ++f) if (b->boost[f] != 1.0) P.boosts_all_one = 0u;
   P.doc_bits = doc_bits; P.bitmap_words = bitmap_words; P.bitmap_sum_words = bitmap_sum_words; P.bitmap_doc_words = bitmap_doc_words;
   P.xcount = b->xcount.p;
+  P.q_binoff = b->q_binoff.p; P.q_shift = b->q_shift.p; P.q_gsegoff = b->q_gsegoff.p;
   P.rec_count = b->counters.p + 1;
   CU(cudaEventRecord(b->ev[2], st));
 
@@ -599,15 +639,15 @@ int batch_run(pb_batch* b) {
       CU(cudaMemsetAsync(b->bitmap.p, 0, b->bitmap.cap * sizeof(uint32_t), st));
       b->bitmap_zeroed = b->bitmap.cap;
     }
-    CU(b->rec_key.ensure(rec_cap)); CU(b->rec_val.ensure(rec_cap));
-    CU(b->rec_key2.ensure(rec_cap)); CU(b->rec_val2.ensure(rec_cap));
+    CU(b->rec.ensure(rec_cap));
     P.segs = b->seg_g.p; P.tile_off = (const uint64_t*)b->g_tile_off.p;
     P.bitmap = b->bitmap.p;
-    P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)rec_cap;
+    P.rec = b->rec.p;
     P.stats = b->stats.p + ST_COUNT;
+    uint64_t legacy_cap = 0;
     // Rounds are planned with an ESTIMATE for exact-scheme queries; the marking pass counts the
-    // real number of diverted rows, and a round that would overflow the record buffers is split
-    // (its marks are cleared first) before anything has been scored.
+    // real capacity of every bin, and a round that would overflow the record buffer is split (its
+    // marks are cleared first) before anything has been scored.
     auto make_round = [&](uint64_t qa, uint64_t qb) {
       return Round{qa, qb, b->h_gsegoff[qa], b->h_gsegoff[qb], b->h_gtileoff[qa], b->h_gtileoff[qb],
                    b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa]};
@@ -620,6 +660,13 @@ int batch_run(pb_batch* b) {
       if (r.sb == r.sa) continue;
       P.seg_begin = (uint32_t)r.sa; P.seg_end = (uint32_t)r.sb; P.tile_begin = r.ta; P.tile_end = r.tb;
       const uint64_t nseg = r.sb - r.sa, tiles = r.tb - r.ta;
+      const uint64_t n_bins = b->h_binoff[r.qb] - b->h_binoff[r.qa];
+      if (n_bins >= 0xFFFFFFF0ull) { pb::set_error("too many side-path bins in one round"); return PB_ERR_UNSUPPORTED; }
+      CU(b->bin_count.ensure(n_bins + 2)); CU(b->bin_off.ensure(n_bins + 2)); CU(b->bin_cursor.ensure(n_bins + 2));
+      P.round_bin0 = b->h_binoff[r.qa]; P.n_bins = (uint32_t)n_bins;
+      P.bin_count = b->bin_count.p; P.bin_off = b->bin_off.p; P.bin_cursor = b->bin_cursor.p;
+      CU(cudaMemsetAsync(b->bin_count.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
+      CU(cudaMemsetAsync(b->bin_cursor.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
       gslot_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, b->q_scheme.p, (uint32_t)r.qa);
       CU(cudaGetLastError());
       int mgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * 8, (tiles + 15) / 16));
@@ -629,10 +676,19 @@ int batch_run(pb_batch* b) {
       ull h_x = 0;
       CU(cudaMemcpyAsync(&h_x, b->xcount.p, sizeof(ull), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
-      const uint64_t need = h_x + (b->h_poff[r.qb] - b->h_poff[r.qa]);
+      const uint64_t need = h_x;                // = sum of the bin capacities
+      auto clear_marks = [&]() -> int {
+        // undo the marks: re-walk the marked rows, or wipe the round's slots when that is less traffic
+        if ((uint64_t)tiles * TILE_ROWS * 4 > r.slots * (uint64_t)bitmap_words * 4) {
+          CU(cudaMemsetAsync(b->bitmap.p, 0, r.slots * (size_t)bitmap_words * sizeof(uint32_t), st));
+        } else {
+          RC(launch_mark(b, P, mgrid, 1));
+          ++launches;
+        }
+        return PB_OK;
+      };
       if (need > rec_cap) {
-        RC(launch_mark(b, P, mgrid, 1));      // undo the marks; nothing was scored yet
-        ++launches;
+        RC(clear_marks());                      // nothing was scored yet
         if (r.qb - r.qa > 1) {
           uint64_t mid = r.qa + (r.qb - r.qa) / 2;
           work.push_back(make_round(mid, r.qb));
@@ -641,15 +697,14 @@ int batch_run(pb_batch* b) {
         }
         if (need > REC_CAP_MAX) { pb::set_error("a single query needs %llu side-path records (> %llu)", (ull)need, (ull)REC_CAP_MAX); return PB_ERR_UNSUPPORTED; }
         rec_cap = need + 1024;
-        CU(b->rec_key.ensure(rec_cap)); CU(b->rec_val.ensure(rec_cap));
-        CU(b->rec_key2.ensure(rec_cap)); CU(b->rec_val2.ensure(rec_cap));
-        P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)rec_cap;
+        CU(b->rec.ensure(rec_cap));
+        P.rec = b->rec.p;
         work.push_back(r);
         continue;
       }
       ++n_rounds;
-      // partial top-k lists this round can add: <= 2 per warp per launch (score, fold) + 2 per query
-      part_bound += 4 * max_warps + 2 * r.slots;
+      // partial top-k lists this round can add: <= 2 per warp per launch (score, bin fold, legacy fold) + 2 per query
+      part_bound += 6 * max_warps + 2 * r.slots;
       if (part_bound > part_cap) {           // rounds were split: grow, keeping the lists written so far
         const uint64_t ncap = part_bound * 2;
         if (ncap >= 0xFFFFFFF0ull) { pb::set_error("too many partial lists"); return PB_ERR_UNSUPPORTED; }
@@ -660,33 +715,47 @@ int batch_run(pb_batch* b) {
         P.out.part_next = b->part_next.p; P.out.part_n = b->part_n.p; P.out.part_doc = b->part_doc.p;
         P.out.part_score = b->part_score.p; P.out.part_cap = (uint32_t)part_cap;
       }
+      if (need) {
+        RC(scan_u32(b, b->bin_count.p, b->bin_off.p, n_bins + 1));
+        ++launches;
+      } else {
+        CU(cudaMemsetAsync(b->bin_off.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
+      }
       RC(launch_score(b, P, true, tiles));
       ++launches;
-      uint32_t h_rec = 0;
-      CU(cudaMemcpyAsync(&h_rec, b->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      if (h_rec > rec_cap) { pb::set_error("side-path record buffer overflow (%u > %llu)", h_rec, (ull)rec_cap); return PB_ERR_INVALID; }
-      if (h_rec) {
-        const int end_bit = (int)std::min<uint32_t>(64, doc_bits + bits_for(std::max<uint64_t>(r.slots, 2)));
-        size_t bytes = 0;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, b->rec_key.p, b->rec_key2.p, b->rec_val.p, b->rec_val2.p,
-                                           (int64_t)h_rec, 0, end_bit, st));
-        CU(b->cub_temp.ensure(bytes));
-        bytes = b->cub_temp.cap;
-        CU(cub::DeviceRadixSort::SortPairs(b->cub_temp.p, bytes, b->rec_key.p, b->rec_key2.p, b->rec_val.p, b->rec_val2.p,
-                                           (int64_t)h_rec, 0, end_bit, st));
-        FoldParams FP;
-        FP.S = P; FP.key = b->rec_key2.p; FP.val = b->rec_val2.p; FP.n = h_rec;
-        RC(launch_fold(b, FP));
-        launches += 2 + (uint32_t)((end_bit + 7) / 8);
+      if (need) {
+        // records of bins that overflow a warp window go through the legacy sorted path
+        overflow_count_kernel<<<(unsigned)std::min<uint64_t>(1024, (n_bins + 255) / 256), 256, 0, st>>>(b->bin_cursor.p, (uint32_t)n_bins, b->counters.p + 3);
+        CU(cudaGetLastError());
+        uint32_t h_over = 0;
+        CU(cudaMemcpyAsync(&h_over, b->counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemsetAsync(b->counters.p + 3, 0, sizeof(uint32_t), st));
+        if (h_over > legacy_cap) {
+          legacy_cap = (uint64_t)h_over + h_over / 4 + 1024;
+          CU(b->rec_key.ensure(legacy_cap)); CU(b->rec_val.ensure(legacy_cap));
+          CU(b->rec_key2.ensure(legacy_cap)); CU(b->rec_val2.ensure(legacy_cap));
+        }
+        P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)legacy_cap;
+        RC(launch_binfold(b, P, n_bins));
+        launches += 2;
+        if (h_over) {
+          const int end_bit = (int)std::min<uint32_t>(64, doc_bits + bits_for(std::max<uint64_t>(r.slots, 2)));
+          size_t bytes = 0;
+          CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, b->rec_key.p, b->rec_key2.p, b->rec_val.p, b->rec_val2.p,
+                                             (int64_t)h_over, 0, end_bit, st));
+          CU(b->cub_temp.ensure(bytes));
+          bytes = b->cub_temp.cap;
+          CU(cub::DeviceRadixSort::SortPairs(b->cub_temp.p, bytes, b->rec_key.p, b->rec_key2.p, b->rec_val.p, b->rec_val2.p,
+                                             (int64_t)h_over, 0, end_bit, st));
+          FoldParams FP;
+          FP.S = P; FP.key = b->rec_key2.p; FP.val = b->rec_val2.p; FP.n = h_over;
+          RC(launch_fold(b, FP));
+          launches += 2 + (uint32_t)((end_bit + 7) / 8);
+          S.legacy_records += h_over;
+        }
       }
-      // undo the marks: re-walk the marked rows, or wipe the round's slots when that is less traffic
-      if ((uint64_t)tiles * TILE_ROWS * 4 > r.slots * (uint64_t)bitmap_words * 4) {
-        CU(cudaMemsetAsync(b->bitmap.p, 0, r.slots * (size_t)bitmap_words * sizeof(uint32_t), st));
-      } else {
-        RC(launch_mark(b, P, mgrid, 1));
-        ++launches;
-      }
+      RC(clear_marks());
       CU(cudaMemsetAsync(b->counters.p + 1, 0, sizeof(uint32_t), st));
     }
     S.side_rounds = n_rounds;
@@ -711,6 +780,7 @@ int batch_run(pb_batch* b) {
   CU(cudaStreamSynchronize(st));
   if (h_cnt[2] & 1u) { pb::set_error("internal: partial top-k list overflow"); return PB_ERR_INVALID; }
   if (h_cnt[2] & 2u) { pb::set_error("internal: side-path record buffer overflow"); return PB_ERR_INVALID; }
+  if (h_cnt[2] & 8u) { pb::set_error("a query expands to more than 2^27 posting lists"); return PB_ERR_UNSUPPORTED; }
   if (h_cnt[2] & 4u) { pb::set_error("a document received more than 64 (query term, expansion) events in one ZeroToOne query"); return PB_ERR_UNSUPPORTED; }
   S.rows_streamed = h_stats[ST_ROWS_STREAMED] + h_stats[ST_COUNT + ST_ROWS_STREAMED];
   S.rows_scored = h_stats[ST_ROWS_SCORED] + h_stats[ST_COUNT + ST_ROWS_SCORED];

@@ -20,6 +20,7 @@
 // and are tabulated on the host with libm (engine.cu), never computed on the device.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 namespace pbk {
@@ -28,6 +29,9 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int TILE_ROWS = 128;          // 32 lanes x 4 rows: one 512 B line group per column
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+#ifndef PB_WINDOW_MAX
+#define PB_WINDOW_MAX 32u      // records a bin-fold window holds; larger bins take the sorted fallback (tests lower it)
+#endif
 #ifndef PB_SCORE_MIN_BLOCKS
 #define PB_SCORE_MIN_BLOCKS 3      // resident CTAs per SM the scoring kernel is compiled for (F <= 2)
 #endif
@@ -135,6 +139,19 @@ struct ScoreParams {
   uint32_t bitmap_sum_words;     // leading summary words of a slot
   uint32_t bitmap_doc_words;     // words of one per-doc bit plane (a slot has two)
   unsigned long long* xcount;    // exact-scheme rows the scoring pass will divert (counted while marking)
+  // Side-path records are written straight into per-query doc-range BINS (no global sort): query q
+  // owns bins [q_binoff[q], q_binoff[q+1]) and doc d falls into bin q_binoff[q] + (d >> q_shift[q]).
+  // The marking pass counts each bin's capacity, a prefix sum gives bin_off, the scoring pass fills.
+  const unsigned long long* q_binoff;
+  const uint8_t* q_shift;
+  const unsigned long long* q_gsegoff;  // first segment of each query (event order = seg - q_gsegoff[q])
+  unsigned long long round_bin0;        // q_binoff of the round's first query
+  uint32_t n_bins;                      // bins of the round
+  uint32_t* bin_count;                  // [n_bins + 1] capacity (marking pass)
+  uint32_t* bin_off;                    // [n_bins + 1] exclusive prefix of bin_count
+  uint32_t* bin_cursor;                 // [n_bins] records written so far
+  uint4* rec;                           // fat records {doc, segment, payload lo, payload hi}
+  // legacy (sorted) records: only for bins that overflow a warp window
   unsigned long long* rec_key;
   unsigned long long* rec_val;
   uint32_t* rec_count;
@@ -529,11 +546,11 @@ __global__ void gfill_kernel(IndexView ix, uint64_t n_qterms, const uint64_t* __
 
 // One thread per query: promote the elected list to PRIMARY and bound the side-path records:
 // every secondary row + at most one primary row per secondary doc.
-__global__ void gprimary_kernel(uint64_t n_queries, const unsigned long long* __restrict__ q_isg,
+__global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const unsigned long long* __restrict__ q_isg,
                                 const unsigned long long* __restrict__ q_grows,
                                 const unsigned long long* __restrict__ q_prim, Seg* __restrict__ seg_g,
-                                unsigned long long* __restrict__ q_recbound, unsigned long long* __restrict__ q_pbound,
-                                uint8_t* __restrict__ q_scheme,
+                                unsigned long long* __restrict__ q_recbound, unsigned long long* __restrict__ q_nbins,
+                                uint8_t* __restrict__ q_scheme, uint8_t* __restrict__ q_shift,
                                 const uint64_t* __restrict__ query_term_off,
                                 const unsigned long long* __restrict__ qt_goff,
                                 unsigned long long* __restrict__ q_gsegoff) {
@@ -541,8 +558,8 @@ __global__ void gprimary_kernel(uint64_t n_queries, const unsigned long long* __
   if (q > n_queries) return;
   q_gsegoff[q] = qt_goff[query_term_off[q]];   // qt_goff has n_qterms + 1 entries
   if (q == n_queries) return;
-  unsigned long long bound = 0, pbound = 0;
-  uint8_t scheme = 0;
+  unsigned long long bound = 0, nbins = 0;
+  uint8_t scheme = 0, shift = 0;
   if (q_isg[q]) {
     unsigned long long p = q_prim[q];
     uint32_t idx = 0xFFFFFFFFu - (uint32_t)(p & 0xFFFFFFFFull);
@@ -555,12 +572,20 @@ __global__ void gprimary_kernel(uint64_t n_queries, const unsigned long long* __
     } else {
       // primary scheme: every secondary row + at most one primary row per secondary doc
       seg_g[idx].mode = MODE_PRIMARY;
-      bound = pbound = 2ull * secondary;
+      bound = 2ull * secondary;
     }
+    // doc-range bins of width 2^shift sized for ~8 records each (a warp window holds 32)
+    const unsigned long long n_docs_pow = 1ull << doc_bits;
+    unsigned long long want = bound / 8 + 1;                 // number of bins wanted
+    uint32_t sh = doc_bits;
+    while (sh > 0 && (n_docs_pow >> sh) < want) --sh;
+    shift = (uint8_t)sh;
+    nbins = (n_docs_pow >> sh);
   }
   q_recbound[q] = bound;
-  q_pbound[q] = pbound;
+  q_nbins[q] = nbins;
   q_scheme[q] = scheme;
+  q_shift[q] = shift;
 }
 
 // Assign bitmap slots for one round: slot = rank of the query among the round's class-G queries.
@@ -612,6 +637,8 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
       uint32_t* ba = sm + P.bitmap_sum_words;
       uint32_t* bb = ba + P.bitmap_doc_words;
       const bool exact = sg.mode == MODE_MULTI;
+      const uint32_t bin_base = (uint32_t)(P.q_binoff[sg.q] - P.round_bin0);
+      const uint32_t shift = P.q_shift[sg.q];
       const uint64_t abs0 = sg.row_begin / TILE_ROWS;
       const uint64_t rend = sg.row_begin + sg.n_rows;
       for (; t < tend; ++t) {
@@ -626,14 +653,22 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
             if (clear) {
               ba[doc >> 5] = 0u; sm[doc >> 15] = 0u;
               if (exact) bb[doc >> 5] = 0u;
-            } else if (!exact) {
-              atomicOr(&ba[doc >> 5], bit);
-              atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
             } else {
-              if (atomicOr(&ba[doc >> 5], bit) & bit) {          // seen before: a multi-event doc
+              // inc = records the scoring pass may write for this row's doc because of this row:
+              // the row itself (+ one more for the doc's first / primary row, counted once)
+              uint32_t inc = 0;
+              if (!exact) {
+                const uint32_t old = atomicOr(&ba[doc >> 5], bit);
+                atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
+                inc = (old & bit) ? 1u : 2u;
+              } else if (atomicOr(&ba[doc >> 5], bit) & bit) {    // seen before: a multi-event doc
                 const uint32_t old = atomicOr(&bb[doc >> 5], bit);
                 atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
-                xcount += (old & bit) ? 1u : 2u;                  // this row (+ the doc's first row)
+                inc = (old & bit) ? 1u : 2u;
+              }
+              if (inc) {
+                atomicAdd(&P.bin_count[bin_base + (doc >> shift)], inc);
+                xcount += inc;
               }
             }
           }
@@ -644,7 +679,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
     ++s;
   }
   xcount = warp_sum_u64(xcount);
-  if (lane == 0 && xcount) atomicAdd(P.xcount, xcount);
+  if (lane == 0 && xcount) atomicAdd(P.xcount, xcount);     // = sum of all bin capacities of the round
 }
 
 // ------------------------------------------------------------------------------------------
@@ -702,6 +737,34 @@ __device__ __forceinline__ void z2o_rows(const uint4 (&tq)[F], const uint4 (&lq)
   }
 }
 
+// ZeroToOne side-path payload: the row's per-field (tf, fl) packed into 63 bits; bit 63 = escape
+// (a value does not fit: the fold recovers the row by binary search and gathers it instead).
+template <int F> struct Z2oPack {
+  static constexpr int TFB = F == 1 ? 20 : F == 2 ? 11 : F == 3 ? 7 : 5;
+  static constexpr int FLB = F == 1 ? 32 : F == 2 ? 20 : F == 3 ? 14 : 10;
+  static_assert((TFB + FLB) * F <= 63, "payload layout");
+};
+template <int F>
+__device__ __forceinline__ unsigned long long z2o_pack(const uint32_t (&tf)[F], const uint32_t (&fl)[F]) {
+  unsigned long long p = 0;
+  bool esc = false;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    esc |= (Z2oPack<F>::TFB < 32 && (tf[f] >> Z2oPack<F>::TFB)) || (Z2oPack<F>::FLB < 32 && (fl[f] >> Z2oPack<F>::FLB));
+    p |= ((unsigned long long)tf[f] | ((unsigned long long)fl[f] << Z2oPack<F>::TFB)) << (f * (Z2oPack<F>::TFB + Z2oPack<F>::FLB));
+  }
+  return esc ? (1ull << 63) : p;
+}
+template <int F>
+__device__ __forceinline__ void z2o_unpack(unsigned long long p, uint32_t (&tf)[F], uint32_t (&fl)[F]) {
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    unsigned long long v = p >> (f * (Z2oPack<F>::TFB + Z2oPack<F>::FLB));
+    tf[f] = (uint32_t)(v & ((1ull << Z2oPack<F>::TFB) - 1ull));
+    fl[f] = (uint32_t)((v >> Z2oPack<F>::TFB) & ((1ull << Z2oPack<F>::FLB) - 1ull));
+  }
+}
+
 // Per-segment state of the scoring loop.
 struct SegCtx {
   uint64_t rbeg, rend;      // absolute row range of the segment
@@ -712,6 +775,8 @@ struct SegCtx {
   uint32_t mode;
   const uint32_t* sum;      // GMODE: the query's summary bits / doc bits
   const uint32_t* bm;
+  uint32_t bin_base;        // GMODE: first bin of the query, relative to the round
+  uint32_t shift;           // GMODE: log2(bin width in docs)
 };
 
 // One tile = 128 aligned rows; lane l owns rows 4l..4l+3 (one 128-bit load per column).
@@ -795,31 +860,27 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const double*
       }
     }
     some &= ~dmask;
-    if (__any_sync(0xffffffffu, dmask != 0)) {
-      const uint32_t c = __popc(dmask);
-      uint32_t incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      uint32_t base = 0;
-      if (lane == 31) base = atomicAdd(P.rec_count, incl);
-      base = __shfl_sync(0xffffffffu, base, 31);
-      uint32_t pos = base + incl - c;
+    if (dmask) {
+      // one fat record per diverted row, written straight into the doc-range bin of the query
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if ((dmask >> j) & 1u) {
-          if (pos < P.rec_cap) {
-            P.rec_key[pos] = ((unsigned long long)C.slot << P.doc_bits) | dv[j];
-            P.rec_val[pos] = ((unsigned long long)C.seg << 32) | (unsigned long long)(uint32_t)(row0 + j);
+          const uint32_t bin = C.bin_base + (dv[j] >> C.shift);
+          const uint32_t pos = P.bin_off[bin] + atomicAdd(&P.bin_cursor[bin], 1u);
+          unsigned long long pay;
+          if (SCORER == 0) {
+            pay = (unsigned long long)__double_as_longlong(sc[j]);     // the event's score (<= 0 / NaN = None)
           } else {
-            atomicOr(P.out.error_flag, 2u);
+            uint32_t tfj[F], flj[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) { tfj[f] = u4c(tq[f], j); flj[f] = u4c(lq[f], j); }
+            pay = z2o_pack<F>(tfj, flj);
           }
-          ++pos;
+          if (pos < P.bin_off[bin + 1]) P.rec[pos] = make_uint4(dv[j], C.seg, (uint32_t)pay, (uint32_t)(pay >> 32));
+          else atomicOr(P.out.error_flag, 2u);
         }
       }
-      st_div += c;
+      st_div += __popc(dmask);
     }
   }
   if (FAST) acc.template add4<false>(P.out, some, dv, sc, lane);
@@ -999,9 +1060,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? PB_SCORE_MIN_BLOCKS : 2
         C.zs = z2o_term_score(explen, sg.qlen);
         C.qtl = (uint32_t)(P.query_term_off[sg.q + 1] - P.query_term_off[sg.q]);
       }
+      C.bin_base = 0; C.shift = 0;
       if (GMODE) {
         C.sum = P.bitmap + (size_t)sg.slot * P.bitmap_words;
         C.bm = C.sum + P.bitmap_sum_words + (sg.mode == MODE_MULTI ? P.bitmap_doc_words : 0u);
+        C.bin_base = (uint32_t)(P.q_binoff[sg.q] - P.round_bin0);
+        C.shift = P.q_shift[sg.q];
       }
       const uint64_t abs0 = C.rbeg / TILE_ROWS;
 #if PB_TMA
@@ -1182,6 +1246,112 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
   return __longlong_as_double((long long)shfl_u64((uint64_t)__double_as_longlong(v), src));
 }
 
+// The fold of one window of <= 32 events (lane = event).  The events of a doc occupy consecutive
+// lanes (`hm` = mask of the lanes that start a doc, `n_act` = lanes in use).  PRESORTED: the lanes
+// of a doc are already in event order (segment order).
+template <int F, int SCORER, bool PRESORTED>
+__device__ __forceinline__ void fold_window(const ScoreParams& P, WarpAcc& acc, int lane, bool in, bool head, uint32_t hm,
+                                            uint32_t advance, uint32_t q, uint32_t doc, unsigned long long val,
+                                            double ev_score, uint32_t e_qti, uint32_t e_term, uint32_t (&tfv)[F],
+                                            uint32_t (&flv)[F]) {
+  // group geometry
+  const int my_head = 31 - __clz(hm & (0xFFFFFFFFu >> (31 - lane)));
+  const uint32_t above = hm & (0xFFFFFFFEu << my_head);
+  const int g_end = above ? (__ffs(above) - 1) : (int)advance;
+  const int size = in ? g_end - my_head : 0;
+  const int pos = lane - my_head;
+  const uint32_t gmask = in ? (((size >= 32) ? 0xFFFFFFFFu : ((1u << size) - 1u)) << my_head) : 0u;
+  int maxsize = size;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxsize = max(maxsize, __shfl_xor_sync(0xffffffffu, maxsize, o));
+
+  // rank of the event inside its doc in processing order
+  int rank = pos;
+  if (!(PRESORTED && SCORER == 0)) {
+  rank = 0;
+  for (int m = 0; m < maxsize; ++m) {
+    const int src = min(my_head + m, 31);
+    const unsigned long long ov = shfl_u64(val, src);
+    bool before;
+    if (SCORER == 0) {
+      before = ov < val;
+    } else {
+      const double os = shfl_f64(ev_score, src);
+      before = os > ev_score || (os == ev_score && ov < val);
+    }
+    if (m < size && m != pos && before) ++rank;
+  }
+  // pull the event that belongs at this lane's position
+  int src = lane;
+  for (int m = 0; m < maxsize; ++m) {
+    const int c = min(my_head + m, 31);
+    const int rc = __shfl_sync(0xffffffffu, rank, c);
+    if (m < size && rc == pos) src = c;
+  }
+  ev_score = shfl_f64(ev_score, src);
+  e_qti = __shfl_sync(0xffffffffu, e_qti, src);
+  e_term = __shfl_sync(0xffffffffu, e_term, src);
+#pragma unroll
+  for (int f = 0; f < F; ++f) { tfv[f] = __shfl_sync(0xffffffffu, tfv[f], src); flv[f] = __shfl_sync(0xffffffffu, flv[f], src); }
+  }
+
+  bool has = false;
+  double result = 0.0;
+  if (SCORER == 0) {
+    uint32_t cur = NONE;
+    for (int m = 0; m < maxsize; ++m) {
+      const int c = min(my_head + m, 31);
+      const double sm = shfl_f64(ev_score, c);
+      const uint32_t qm = __shfl_sync(0xffffffffu, e_qti, c);
+      if (m < size) {
+        const bool firstq = qm != cur;
+        cur = qm;
+        if (sm > 0.0) {                          // None otherwise: the doc is only marked visited
+          if (!has) { result = sm; has = true; }
+          else if (firstq) result = __dadd_rn(result, sm);
+          else result = fmax(result, sm);
+        }
+      }
+    }
+  } else {
+    has = in;
+    const uint32_t qtl = in ? (uint32_t)(P.query_term_off[q + 1] - P.query_term_off[q]) : 0u;
+#pragma unroll
+    for (int x = 0; x < F; ++x) {
+      double accx = 0.0;
+      bool accepted = false;                     // this lane's entry was accepted for field x
+      for (int m = 0; m < maxsize; ++m) {
+        const int c = min(my_head + m, 31);
+        const uint32_t c_qti = __shfl_sync(0xffffffffu, e_qti, c);
+        const uint32_t c_term = __shfl_sync(0xffffffffu, e_term, c);
+        const uint32_t c_tf = __shfl_sync(0xffffffffu, tfv[x], c);
+        const uint32_t conflict = __ballot_sync(0xffffffffu, accepted && e_qti == c_qti) & gmask;
+        const uint32_t used = __popc(__ballot_sync(0xffffffffu, accepted && e_term == c_term) & gmask);
+        const bool ok = m < size && c_tf > 0 && conflict == 0u && used < c_tf;
+        double contrib = 0.0;
+        if (ok && pos == m) { accepted = true; contrib = z2o_entry(ev_score, tfv[x], flv[x], qtl); }
+        contrib = shfl_f64(contrib, c);
+        if (ok) accx = __dadd_rn(accx, contrib);
+      }
+      result = fmax(accx, result);
+    }
+  }
+  has = has && head;
+  // emit: lanes may belong to different queries (sorted, so at most a few switches)
+  uint32_t mres = __ballot_sync(0xffffffffu, has);
+  while (mres) {
+    int l = __ffs(mres) - 1;
+    uint32_t ql = __shfl_sync(0xffffffffu, q, l);
+    bool mine = has && q == ql;
+    if (acc.q != ql) {
+      if (acc.q != NONE) acc.flush(P.out, false, lane);
+      acc.reset(ql);
+    }
+    acc.add(P.out, mine, doc, result, lane);
+    mres &= ~__ballot_sync(0xffffffffu, mine);
+  }
+}
+
 // Warp-cooperative fold.  A warp walks its span of the sorted records in windows of 32: lane =
 // record.  Every lane gathers its own event (segment descriptor, posting row) — 32 independent
 // gathers in flight — then the events of a doc (consecutive lanes) are put in processing order
@@ -1250,17 +1420,6 @@ __global__ void __launch_bounds__(CTA_THREADS) fold_kernel(const __grid_constant
       hm &= (1u << lim) - 1u;
     }
     const uint32_t advance = min(lim, n_in);
-    // group geometry
-    const int my_head = 31 - __clz(hm & (0xFFFFFFFFu >> (31 - lane)));
-    const uint32_t above = hm & (0xFFFFFFFEu << my_head);
-    const int g_end = above ? (__ffs(above) - 1) : (int)advance;
-    const int size = in ? g_end - my_head : 0;
-    const int pos = lane - my_head;
-    const uint32_t gmask = in ? (((size >= 32) ? 0xFFFFFFFFu : ((1u << size) - 1u)) << my_head) : 0u;
-    int maxsize = size;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxsize = max(maxsize, __shfl_xor_sync(0xffffffffu, maxsize, o));
-
     // every lane gathers its own event
     unsigned long long val = in ? FP.val[i] : 0ull;
     Seg sg;
@@ -1282,89 +1441,149 @@ __global__ void __launch_bounds__(CTA_THREADS) fold_kernel(const __grid_constant
         for (int f = 0; f < F; ++f) { tfv[f] = row_tf<F>(P.ix.post_blocks, row, f); flv[f] = row_fl<F>(P.ix.post_blocks, row, f); }
       }
     }
-    // rank of the event inside its doc in processing order
-    int rank = 0;
-    for (int m = 0; m < maxsize; ++m) {
-      const int src = min(my_head + m, 31);
-      const unsigned long long ov = shfl_u64(val, src);
-      bool before;
-      if (SCORER == 0) {
-        before = ov < val;
-      } else {
-        const double os = shfl_f64(ev_score, src);
-        before = os > ev_score || (os == ev_score && ov < val);
-      }
-      if (m < size && m != pos && before) ++rank;
-    }
-    // pull the event that belongs at this lane's position
-    int src = lane;
-    for (int m = 0; m < maxsize; ++m) {
-      const int c = min(my_head + m, 31);
-      const int rc = __shfl_sync(0xffffffffu, rank, c);
-      if (m < size && rc == pos) src = c;
-    }
-    ev_score = shfl_f64(ev_score, src);
-    uint32_t e_qti = __shfl_sync(0xffffffffu, (uint32_t)sg.qti, src);
-    uint32_t e_term = __shfl_sync(0xffffffffu, sg.term, src);
-#pragma unroll
-    for (int f = 0; f < F; ++f) { tfv[f] = __shfl_sync(0xffffffffu, tfv[f], src); flv[f] = __shfl_sync(0xffffffffu, flv[f], src); }
-
-    bool has = false;
-    double result = 0.0;
-    if (SCORER == 0) {
-      uint32_t cur = NONE;
-      for (int m = 0; m < maxsize; ++m) {
-        const int c = min(my_head + m, 31);
-        const double sm = shfl_f64(ev_score, c);
-        const uint32_t qm = __shfl_sync(0xffffffffu, e_qti, c);
-        if (m < size) {
-          const bool firstq = qm != cur;
-          cur = qm;
-          if (sm > 0.0) {                          // None otherwise: the doc is only marked visited
-            if (!has) { result = sm; has = true; }
-            else if (firstq) result = __dadd_rn(result, sm);
-            else result = fmax(result, sm);
-          }
-        }
-      }
-    } else {
-      has = in;
-      const uint32_t qtl = in ? (uint32_t)(P.query_term_off[q + 1] - P.query_term_off[q]) : 0u;
-#pragma unroll
-      for (int x = 0; x < F; ++x) {
-        double accx = 0.0;
-        bool accepted = false;                     // this lane's entry was accepted for field x
-        for (int m = 0; m < maxsize; ++m) {
-          const int c = min(my_head + m, 31);
-          const uint32_t c_qti = __shfl_sync(0xffffffffu, e_qti, c);
-          const uint32_t c_term = __shfl_sync(0xffffffffu, e_term, c);
-          const uint32_t c_tf = __shfl_sync(0xffffffffu, tfv[x], c);
-          const uint32_t conflict = __ballot_sync(0xffffffffu, accepted && e_qti == c_qti) & gmask;
-          const uint32_t used = __popc(__ballot_sync(0xffffffffu, accepted && e_term == c_term) & gmask);
-          const bool ok = m < size && c_tf > 0 && conflict == 0u && used < c_tf;
-          double contrib = 0.0;
-          if (ok && pos == m) { accepted = true; contrib = z2o_entry(ev_score, tfv[x], flv[x], qtl); }
-          contrib = shfl_f64(contrib, c);
-          if (ok) accx = __dadd_rn(accx, contrib);
-        }
-        result = fmax(accx, result);
-      }
-    }
-    has = has && head;
-    // emit: lanes may belong to different queries (sorted, so at most a few switches)
-    uint32_t mres = __ballot_sync(0xffffffffu, has);
-    while (mres) {
-      int l = __ffs(mres) - 1;
-      uint32_t ql = __shfl_sync(0xffffffffu, q, l);
-      bool mine = has && q == ql;
-      if (acc.q != ql) {
-        if (acc.q != NONE) acc.flush(P.out, false, lane);
-        acc.reset(ql);
-      }
-      acc.add(P.out, mine, doc, result, lane);
-      mres &= ~__ballot_sync(0xffffffffu, mine);
-    }
+    fold_window<F, SCORER, false>(P, acc, lane, in, head, hm, advance, q, doc, val, ev_score, (uint32_t)sg.qti, sg.term, tfv, flv);
     base += advance;
+  }
+  if (acc.q != NONE) acc.flush(P.out, false, lane);
+}
+
+// Row of `doc` inside a segment's posting list (docs ascend): used only on fallback paths.
+template <int F>
+__device__ __forceinline__ uint32_t find_row(const ScoreParams& P, const Seg& sg, uint32_t doc) {
+  uint64_t lo = sg.row_begin, hi = sg.row_begin + sg.n_rows;
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (row_doc<F>(P.ix.post_blocks, mid) < doc) lo = mid + 1; else hi = mid;
+  }
+  return (uint32_t)lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bin fold: the side path without a global sort.  The scoring pass has written the diverted
+// events as fat records into per-query doc-range bins sized for ~8 records.  A warp packs as
+// many consecutive whole bins as fit into its 32 lanes (lane = record), orders the window by
+// (bin, doc, event order) with a 15-step bitonic network of shuffles, and folds every doc with
+// fold_window.  Nothing is gathered from the posting columns: BM25 records carry the score,
+// ZeroToOne records carry the packed (tf, fl).  A bin holding more than 32 records (doc ids
+// clustered far beyond the uniform expectation) is handed to the legacy sorted path.
+// ------------------------------------------------------------------------------------------
+template <int F, int SCORER>
+__global__ void __launch_bounds__(CTA_THREADS) binfold_kernel(const __grid_constant__ ScoreParams P) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t b = (uint32_t)(((uint64_t)P.n_bins * w) / W);
+  const uint32_t b1 = (uint32_t)(((uint64_t)P.n_bins * (w + 1)) / W);
+  WarpAcc acc;
+  acc.reset(NONE);
+  while (b < b1) {
+    // lane l looks at bin b + l
+    const uint32_t bl = b + lane;
+    const uint32_t cnt = bl < b1 ? P.bin_cursor[bl] : 64u;
+    const uint32_t boff = bl < b1 ? P.bin_off[bl] : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t take = __ballot_sync(0xffffffffu, incl <= PB_WINDOW_MAX && bl < b1);   // a prefix of the lanes
+    const int nb_take = __popc(take);
+    if (nb_take == 0) {
+      // bin b alone overflows a window: hand its records to the legacy sorted path
+      const uint32_t c0 = __shfl_sync(0xffffffffu, cnt, 0), o0 = __shfl_sync(0xffffffffu, boff, 0);
+      for (uint32_t i = lane; i < c0; i += 32) {
+        const uint4 r = P.rec[o0 + i];
+        const Seg sg = P.segs[r.y];
+        const uint32_t row = find_row<F>(P, sg, r.x);
+        const uint32_t pos = atomicAdd(P.rec_count, 1u);
+        if (pos < P.rec_cap) {
+          P.rec_key[pos] = ((unsigned long long)sg.slot << P.doc_bits) | r.x;
+          P.rec_val[pos] = ((unsigned long long)r.y << 32) | row;
+        } else {
+          atomicOr(P.out.error_flag, 2u);
+        }
+      }
+      b += 1;
+      continue;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, nb_take - 1);
+    if (total == 0) { b += nb_take; continue; }
+    // record lane i -> (bin t, index inside the bin)
+    const bool in = lane < (int)total;
+    int lo = 0, hi = nb_take;             // smallest t with incl[t] > lane
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {             // a range of up to 32 bins needs 6 halvings
+      const int mid = (lo + hi) >> 1;
+      const uint32_t v = __shfl_sync(0xffffffffu, incl, min(mid, 31));
+      if (lo < hi) { if (v <= (uint32_t)lane) lo = mid + 1; else hi = mid; }
+    }
+    const int t = min(lo, nb_take - 1);
+    const uint32_t t_incl = __shfl_sync(0xffffffffu, incl, t), t_cnt = __shfl_sync(0xffffffffu, cnt, t);
+    const uint32_t t_off = __shfl_sync(0xffffffffu, boff, t);
+    uint4 r = make_uint4(0, 0, 0, 0);
+    Seg sg;
+    sg.q = NONE; sg.qti = 0; sg.term = 0; sg.qlen = 0; sg.row_begin = 0; sg.n_rows = 0; sg.slot = 0;
+    unsigned long long key = ~0ull;
+    if (in) {
+      r = P.rec[t_off + (lane - (t_incl - t_cnt))];
+#ifdef PB_DEBUG_PHANTOM
+      if (r.x == 0 && r.y == 0 && r.z == 0 && r.w == 0)
+        printf("phantom: bin %u (+%d) cnt %u off %u cap_end %u idx %u lane %d total %u nb_take %d b %u b1 %u\n", b + t, t, t_cnt, t_off,
+               P.bin_off[b + t + 1], lane - (t_incl - t_cnt), lane, total, nb_take, b, b1);
+#endif
+      sg = P.segs[r.y];
+      const unsigned long long segrel = (unsigned long long)r.y - P.q_gsegoff[sg.q];
+      if (segrel >> 27) atomicOr(P.out.error_flag, 8u);       // > 2^27 posting lists in one query
+      key = ((unsigned long long)t << 59) | ((unsigned long long)r.x << 27) | (segrel & 0x7FFFFFFull);
+    }
+    // bitonic sort of the window by key; `src` remembers where each record came from
+    int src = lane;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const unsigned long long okey = shfl_u64(key, lane ^ j);
+        const int osrc = __shfl_xor_sync(0xffffffffu, src, j);
+        const bool asc = (lane & k) == 0, lower = (lane & j) == 0;
+        const bool other_less = okey < key || (okey == key && osrc < src);
+        if ((lower == asc) == other_less) { key = okey; src = osrc; }
+      }
+    }
+    // bring the payload along
+    const uint32_t s_seg = __shfl_sync(0xffffffffu, r.y, src);
+    const unsigned long long pay = shfl_u64(((unsigned long long)r.w << 32) | r.z, src);
+    const uint32_t q = __shfl_sync(0xffffffffu, sg.q, src);
+    const uint32_t e_qti = __shfl_sync(0xffffffffu, (uint32_t)sg.qti, src);
+    const uint32_t e_term = __shfl_sync(0xffffffffu, sg.term, src);
+    const uint32_t e_qlen = __shfl_sync(0xffffffffu, sg.qlen, src);
+    const uint32_t doc = (uint32_t)(key >> 27);
+    const unsigned long long gk = key >> 27;                      // (bin, doc)
+    const unsigned long long gk_up = __shfl_up_sync(0xffffffffu, gk, 1);
+    const bool head = in && (lane == 0 || gk_up != gk);
+    const uint32_t hm = __ballot_sync(0xffffffffu, head);
+    double ev_score = 0.0;
+    uint32_t tfv[F], flv[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) { tfv[f] = 0; flv[f] = 0; }
+    if (in) {
+      if (SCORER == 0) {
+        ev_score = __longlong_as_double((long long)pay);
+      } else {
+        ev_score = z2o_term_score(P.ix.term_byte_len[e_term], e_qlen);
+        if (pay >> 63) {                                           // escape: gather the row
+          const Seg sg2 = P.segs[s_seg];
+          const uint32_t row = find_row<F>(P, sg2, doc);
+#pragma unroll
+          for (int f = 0; f < F; ++f) { tfv[f] = row_tf<F>(P.ix.post_blocks, row, f); flv[f] = row_fl<F>(P.ix.post_blocks, row, f); }
+        } else {
+          z2o_unpack<F>(pay, tfv, flv);
+        }
+      }
+    }
+    fold_window<F, SCORER, true>(P, acc, lane, in, head, hm, total, q, doc, (unsigned long long)lane, ev_score, e_qti, e_term,
+                                 tfv, flv);
+    b += nb_take;
   }
   if (acc.q != NONE) acc.flush(P.out, false, lane);
 }
