@@ -377,7 +377,7 @@ def main():
                 "gpu_launches": int(st["gpu_launches"]) * args.steps,
                 "stage_ms": {kk: st[kk] for kk in ("ms_descend", "ms_plan", "ms_score", "ms_side", "ms_finalize")},
                 "rows": {"scored_per_step": rows_all, "streamed_direct": st["rows_streamed_direct"],
-                         "diverted": st["rows_diverted"], "results": res_all, "side_rounds": st["side_rounds"]},
+                         "diverted": st["rows_diverted"], "legacy_records": st.get("legacy_records"), "results": res_all, "side_rounds": st["side_rounds"]},
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -173,9 +173,9 @@ typedef struct pb_query_batch_desc {
 
 /* Per-query outputs.  Any pointer may be NULL (that output is skipped).
  * Digests (order independent, wrap-around sums over the result set):
- *   a(d)        = x = (u32)(d+1) * 0x9E3779B1; x ^= x >> 16; x >>= 2              (30-bit)
- *   doc_digest  = sum over the result set of a(d)                                  (64-bit sum)
- *   score_digest= sum of y,  y = lo(s) ^ hi(s)*0x85EBCA77 ^ a(d); y ^= y >> 15; y >>= 2 (64-bit sum)
+ *   a(d)        = (u32)(d+1) * 0x9E3779B1                                          (32-bit, wraps)
+ *   doc_digest  = sum over the result set of (u64)a(d) * a(d)                      (64-bit sum)
+ *   score_digest= sum of (u64)y * y,  y = lo(s) ^ (u32)(hi(s)*0x85EBCA77) ^ a(d)   (64-bit sum)
  *                 (lo/hi = the two 32-bit halves of the f64 score's bit pattern)
  * top-k rows are ordered (score desc, doc ordinal asc) — the reference's comparison rule
  * (src/lib.rs:54-58) when ordinals follow key order. */

@@ -647,16 +647,13 @@ struct ZeroToOne {
 
 // Order-independent digests shared (by definition, not by code) with the GPU
 // path: see include/probly_b200.h "Digests".
-static inline uint32_t doc_mix(uint64_t doc) {
-  uint32_t a = ((uint32_t)doc + 1u) * 0x9E3779B1u;
-  return (a ^ (a >> 16)) >> 2;
-}
-static inline uint64_t doc_hash(uint64_t doc) { return doc_mix(doc); }
+static inline uint32_t doc_mix(uint64_t doc) { return ((uint32_t)doc + 1u) * 0x9E3779B1u; }
+static inline uint64_t doc_hash(uint64_t doc) { uint64_t a = doc_mix(doc); return a * a; }
 static inline uint64_t score_hash(uint64_t doc, double score) {
   uint64_t b; std::memcpy(&b, &score, 8);
   uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
-  uint32_t y = lo ^ (hi * 0x85EBCA77u) ^ doc_mix(doc);
-  return (y ^ (y >> 15)) >> 2;
+  uint64_t y = lo ^ (hi * 0x85EBCA77u) ^ doc_mix(doc);
+  return y * y;
 }
 
 }  // namespace orc

@@ -15,7 +15,7 @@ WLIB = os.path.join(OUT, "libprobly_workload.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-cudart", "shared",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-cudart", "shared", "-diag-suppress", "63,177",
 ]
 
 

@@ -9,6 +9,7 @@
 // There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -203,7 +204,7 @@ struct pb_batch {
   DBuf<uint64_t> term_byte_off, query_term_off;
   // plan
   DBuf<uint32_t> qt_lo, qt_hi, qt_len, qt_q;
-  DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_nbins, q_binoff, q_gsegoff, q_gtileoff;
+  DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_nbins, q_binoff, q_gsegoff, q_gtileoff, q_bmwords, q_bmoff;
   DBuf<uint8_t> q_scheme, q_shift;
   DBuf<ull> xcount;
   DBuf<uint32_t> bin_count, bin_off, bin_cursor;
@@ -228,7 +229,7 @@ struct pb_batch {
   uint32_t tab_tfcap[4] = {}, tab_flcap[4] = {}, tab_off[4] = {}, tab_total = 0;
   bool tab_full = false;
   // host staging
-  std::vector<ull> h_recoff, h_binoff, h_gidx, h_gsegoff, h_gtileoff;
+  std::vector<ull> h_recoff, h_binoff, h_gidx, h_gsegoff, h_gtileoff, h_bmoff;
   pb_batch_stats st{};
 
   ~pb_batch() {
@@ -360,7 +361,7 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   CU(b->qt_gcount.ensure(NT + 2)); CU(b->qt_goff.ensure(NT + 2));
   CU(b->q_isg.ensure(Q + 2)); CU(b->q_gidx.ensure(Q + 2)); CU(b->q_grows.ensure(Q + 2)); CU(b->q_prim.ensure(Q + 2));
   CU(b->q_recbound.ensure(Q + 2)); CU(b->q_recoff.ensure(Q + 2)); CU(b->q_nbins.ensure(Q + 2)); CU(b->q_binoff.ensure(Q + 2));
-  CU(b->q_scheme.ensure(Q + 2)); CU(b->q_shift.ensure(Q + 2)); CU(b->xcount.ensure(2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
+  CU(b->q_scheme.ensure(Q + 2)); CU(b->q_shift.ensure(Q + 2)); CU(b->xcount.ensure(4)); CU(b->q_bmwords.ensure(Q + 2)); CU(b->q_bmoff.ensure(Q + 2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
   CU(b->s_tiles.ensure(Q + 2)); CU(b->s_tile_off.ensure(Q + 2));
   CU(b->seg_s.ensure(Q + 1));
   CU(b->n_results.ensure(Q + 1)); CU(b->doc_digest.ensure(Q + 1)); CU(b->score_digest.ensure(Q + 1));
@@ -382,17 +383,15 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
 }
 
 template <int F, int SC, bool G>
-int launch_score_t(pb_batch* b, const ScoreParams& P, int grid) {
-  size_t smem = score_smem_bytes<F>(P.tab_total);
-  CU(cudaFuncSetAttribute(score_kernel<F, SC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  score_kernel<F, SC, G><<<grid, CTA_THREADS, smem, b->stream>>>(P);
+int launch_score_t(pb_batch* b, const ScoreParams& P, int grid, int threads, size_t smem) {
+  score_kernel<F, SC, G><<<grid, threads, smem, b->stream>>>(P);
   CU(cudaGetLastError());
   return PB_OK;
 }
 template <int F, int SC, bool G>
-int occupancy_score_t(int* per_sm, size_t smem) {
+int occupancy_score_t(int* per_sm, int threads, size_t smem) {
   CU(cudaFuncSetAttribute(score_kernel<F, SC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G>, CTA_THREADS, smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G>, threads, smem));
   return PB_OK;
 }
 
@@ -414,20 +413,42 @@ int dispatch_fs(uint32_t F, uint32_t scorer, Fn&& fn) {
   }
 }
 
-int launch_score(pb_batch* b, const ScoreParams& P, bool gmode, uint64_t tiles) {
+// Shared-memory plan of the scoring kernel: how many copies of the BM25 table (16 = conflict-free
+// LDS.64, see ScoreParams::tab_rep_shift) fit, and the CTA shape that keeps ~24 warps per SM resident.
+struct ScorePlan { uint32_t rep_shift; int threads; size_t smem; };
+ScorePlan score_plan(const pb_batch* b, uint32_t tab_total) {
+  ScorePlan sp{0, 256, 0};
+  if (tab_total == 0) return sp;
+  const size_t budget = 220u << 10;                 // of the 227 KB a CTA may use
+  uint32_t want = 4;                                // 16 copies
+  if (const char* e = std::getenv("PB_TAB_REP_SHIFT")) want = (uint32_t)std::min(4, std::max(0, atoi(e)));
+  uint32_t sh = want;
+  while (sh > 0 && (((size_t)tab_total * 8) << sh) > budget) --sh;
+  sp.rep_shift = sh;
+  sp.smem = (((size_t)tab_total * 8) << sh) + 128;
+  sp.threads = sp.smem <= (72u << 10) ? 256 : sp.smem <= (110u << 10) ? 384 : SCORE_MAX_THREADS;
+  (void)b;
+  return sp;
+}
+
+int launch_score(pb_batch* b, ScoreParams& P, bool gmode, uint64_t tiles) {
   return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
     constexpr int F = decltype(f)::value, SC = decltype(sc)::value;
-    const size_t smem = score_smem_bytes<F>(P.tab_total);
+    const ScorePlan sp = score_plan(b, P.tab_total);
+    P.tab_rep_shift = sp.rep_shift;
+    P.tab_stride = 8u << sp.rep_shift;
+    for (int x = 0; x < 4; ++x) P.tab_boff[x] = P.tab_off[x] * P.tab_stride;
     int per_sm = 1;
-    if (gmode) RC((occupancy_score_t<F, SC, true>(&per_sm, smem)));
-    else RC((occupancy_score_t<F, SC, false>(&per_sm, smem)));
-    if (per_sm < 1) per_sm = 1;
+    if (gmode) RC((occupancy_score_t<F, SC, true>(&per_sm, sp.threads, sp.smem)));
+    else RC((occupancy_score_t<F, SC, false>(&per_sm, sp.threads, sp.smem)));
+    if (per_sm < 1) { pb::set_error("scoring kernel does not fit an SM (%d threads, %zu B shared)", sp.threads, sp.smem); return PB_ERR_CUDA; }
     // one warp = one contiguous span of tiles; never more warps than there is work for
+    const uint64_t warps_per_cta = (uint64_t)sp.threads / 32;
     uint64_t max_grid = (uint64_t)b->ix->sm_count * per_sm;
-    uint64_t want = (tiles + WARPS_PER_CTA * 2 - 1) / (WARPS_PER_CTA * 2);
+    uint64_t want = (tiles + warps_per_cta * 2 - 1) / (warps_per_cta * 2);
     int grid = (int)std::max<uint64_t>(1, std::min(max_grid, want));
-    if (gmode) return launch_score_t<F, SC, true>(b, P, grid);
-    return launch_score_t<F, SC, false>(b, P, grid);
+    if (gmode) return launch_score_t<F, SC, true>(b, P, grid, sp.threads, sp.smem);
+    return launch_score_t<F, SC, false>(b, P, grid, sp.threads, sp.smem);
   });
 }
 
@@ -527,13 +548,13 @@ int batch_run(pb_batch* b) {
   if (n_gsegs >= 0xFFFFFFF0ull) { pb::set_error("batch expands to more than 2^32 posting lists"); return PB_ERR_UNSUPPORTED; }
   S.n_segments = n_gsegs;   // class-S segments are added below from the stats
 
-  struct Round { uint64_t qa, qb, sa, sb, ta, tb, slots, recs; };
+  struct Round { uint64_t qa, qb, sa, sb, ta, tb, slots, recs, words; };
   std::vector<Round> rounds;
   const uint32_t doc_bits = bits_for(std::max<uint64_t>(ix->n_docs, 2));
   const uint32_t bitmap_sum_words = (uint32_t)(ix->n_docs / 32768 + 1);
   const uint32_t bitmap_doc_words = (uint32_t)((ix->n_docs + 31) / 32 + 1);
   const uint32_t bitmap_words = bitmap_sum_words + 2 * bitmap_doc_words;
-  uint64_t rec_cap = 0, slot_cap = 0;
+  uint64_t rec_cap = 0, pool_words = 0;
   if (n_gsegs) {
     CU(b->seg_g.ensure(n_gsegs + 1));
     CU(b->g_tiles.ensure(n_gsegs + 2));
@@ -542,19 +563,22 @@ int batch_run(pb_batch* b) {
                                                    b->qt_q.p, b->qt_gcount.p, b->qt_goff.p, b->seg_g.p, b->g_tiles.p,
                                                    b->q_prim.p, b->stats.p + ST_COUNT);
     CU(cudaGetLastError());
+    CU(cudaMemsetAsync(b->q_bmwords.p, 0, (Q + 2) * sizeof(ull), st));
     gprimary_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q, doc_bits, b->q_isg.p, b->q_grows.p, b->q_prim.p,
                                                                      b->seg_g.p, b->q_recbound.p, b->q_nbins.p, b->q_scheme.p,
                                                                      b->q_shift.p, b->query_term_off.p, b->qt_goff.p,
-                                                                     b->q_gsegoff.p);
+                                                                     b->q_gsegoff.p, b->q_bmwords.p, bitmap_words);
     CU(cudaGetLastError());
     RC(scan_ull(b, b->g_tiles.p, b->g_tile_off.p, n_gsegs + 1));
     RC(scan_ull(b, b->q_recbound.p, b->q_recoff.p, Q + 1));
     RC(scan_ull(b, b->q_nbins.p, b->q_binoff.p, Q + 1));
     RC(scan_ull(b, b->q_isg.p, b->q_gidx.p, Q + 1));
+    RC(scan_ull(b, b->q_bmwords.p, b->q_bmoff.p, Q + 1));
     gather_tileoff_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q + 1, b->q_gsegoff.p, b->g_tile_off.p, b->q_gtileoff.p);
     CU(cudaGetLastError());
-    launches += 7;
-    b->h_binoff.resize(Q + 1);
+    launches += 8;
+    b->h_binoff.resize(Q + 1); b->h_bmoff.resize(Q + 1);
+    CU(cudaMemcpyAsync(b->h_bmoff.data(), b->q_bmoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     b->h_recoff.resize(Q + 1); b->h_gidx.resize(Q + 1); b->h_gsegoff.resize(Q + 1); b->h_gtileoff.resize(Q + 1);
     CU(cudaMemcpyAsync(b->h_recoff.data(), b->q_recoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_binoff.data(), b->q_binoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -563,19 +587,22 @@ int batch_run(pb_batch* b) {
     CU(cudaMemcpyAsync(b->h_gtileoff.data(), b->q_gtileoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     // rounds: contiguous query ranges whose record bound and bitmap slots fit the workspace
-    slot_cap = std::max<uint64_t>(1, BITMAP_POOL_BYTES / ((uint64_t)bitmap_words * 4));
+    pool_words = BITMAP_POOL_BYTES / 4;
     rec_cap = REC_CAP_DEFAULT;
-    for (uint64_t q = 0; q < Q; ++q) rec_cap = std::max<uint64_t>(rec_cap, b->h_recoff[q + 1] - b->h_recoff[q]);
+    for (uint64_t q = 0; q < Q; ++q) {
+      rec_cap = std::max<uint64_t>(rec_cap, b->h_recoff[q + 1] - b->h_recoff[q]);
+      pool_words = std::max<uint64_t>(pool_words, b->h_bmoff[q + 1] - b->h_bmoff[q]);     // one query always fits
+    }
     if (rec_cap > REC_CAP_MAX) { pb::set_error("a single query needs %llu side-path records (> %llu)", (ull)rec_cap, (ull)REC_CAP_MAX); return PB_ERR_UNSUPPORTED; }
     uint64_t qa = 0;
     while (qa < Q) {
-      // largest qb with recoff[qb]-recoff[qa] <= rec_cap and gidx[qb]-gidx[qa] <= slot_cap
+      // largest qb with recoff[qb]-recoff[qa] <= rec_cap and bmoff[qb]-bmoff[qa] <= pool_words
       uint64_t qb1 = std::upper_bound(b->h_recoff.begin() + qa, b->h_recoff.end(), b->h_recoff[qa] + rec_cap) - b->h_recoff.begin() - 1;
-      uint64_t qb2 = std::upper_bound(b->h_gidx.begin() + qa, b->h_gidx.end(), b->h_gidx[qa] + slot_cap) - b->h_gidx.begin() - 1;
+      uint64_t qb2 = std::upper_bound(b->h_bmoff.begin() + qa, b->h_bmoff.end(), b->h_bmoff[qa] + pool_words) - b->h_bmoff.begin() - 1;
       uint64_t qb3 = std::upper_bound(b->h_binoff.begin() + qa, b->h_binoff.end(), b->h_binoff[qa] + BIN_CAP) - b->h_binoff.begin() - 1;
       uint64_t qb = std::max<uint64_t>(qa + 1, std::min(qb1, std::min(qb2, qb3)));
       Round r{qa, qb, b->h_gsegoff[qa], b->h_gsegoff[qb], b->h_gtileoff[qa], b->h_gtileoff[qb],
-              b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa]};
+              b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa], b->h_bmoff[qb] - b->h_bmoff[qa]};
       if (r.sb > r.sa) rounds.push_back(r);
       qa = qb;
     }
@@ -613,7 +640,8 @@ int batch_run(pb_batch* b) {
   P.boosts_all_one = 1u;
   for (uint32_t f = 0; f < ix->F; ++f) if (b->boost[f] != 1.0) P.boosts_all_one = 0u;
   P.doc_bits = doc_bits; P.bitmap_words = bitmap_words; P.bitmap_sum_words = bitmap_sum_words; P.bitmap_doc_words = bitmap_doc_words;
-  P.xcount = b->xcount.p;
+  P.xcount = b->xcount.p; P.xtiles = b->xcount.p + 1;
+  P.q_bmoff = b->q_bmoff.p; P.q_prim = b->q_prim.p;
   P.q_binoff = b->q_binoff.p; P.q_shift = b->q_shift.p; P.q_gsegoff = b->q_gsegoff.p;
   P.rec_count = b->counters.p + 1;
   CU(cudaEventRecord(b->ev[2], st));
@@ -631,10 +659,9 @@ int batch_run(pb_batch* b) {
 
   // ---- class G: rounds of the side path --------------------------------------------------
   if (!rounds.empty()) {
-    uint64_t max_slots = 0;
-    for (auto& r : rounds) max_slots = std::max(max_slots, r.slots);
-    const size_t bm_words_total = (size_t)max_slots * bitmap_words;
-    CU(b->bitmap.ensure(bm_words_total + 1));
+    uint64_t bm_words_total = 0;
+    for (auto& r : rounds) bm_words_total = std::max(bm_words_total, r.words);
+    CU(b->bitmap.ensure(bm_words_total + 8));
     if (b->bitmap_zeroed < b->bitmap.cap) {      // freshly (re)allocated: zero once; rounds clean up after themselves
       CU(cudaMemsetAsync(b->bitmap.p, 0, b->bitmap.cap * sizeof(uint32_t), st));
       b->bitmap_zeroed = b->bitmap.cap;
@@ -650,7 +677,7 @@ int batch_run(pb_batch* b) {
     // marks are cleared first) before anything has been scored.
     auto make_round = [&](uint64_t qa, uint64_t qb) {
       return Round{qa, qb, b->h_gsegoff[qa], b->h_gsegoff[qb], b->h_gtileoff[qa], b->h_gtileoff[qb],
-                   b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa]};
+                   b->h_gidx[qb] - b->h_gidx[qa], b->h_recoff[qb] - b->h_recoff[qa], b->h_bmoff[qb] - b->h_bmoff[qa]};
     };
     std::vector<Round> work(rounds.rbegin(), rounds.rend());
     uint32_t n_rounds = 0;
@@ -664,23 +691,28 @@ int batch_run(pb_batch* b) {
       if (n_bins >= 0xFFFFFFF0ull) { pb::set_error("too many side-path bins in one round"); return PB_ERR_UNSUPPORTED; }
       CU(b->bin_count.ensure(n_bins + 2)); CU(b->bin_off.ensure(n_bins + 2)); CU(b->bin_cursor.ensure(n_bins + 2));
       P.round_bin0 = b->h_binoff[r.qa]; P.n_bins = (uint32_t)n_bins;
+      P.round_bm0 = b->h_bmoff[r.qa];
       P.bin_count = b->bin_count.p; P.bin_off = b->bin_off.p; P.bin_cursor = b->bin_cursor.p;
       CU(cudaMemsetAsync(b->bin_count.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
       CU(cudaMemsetAsync(b->bin_cursor.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
       gslot_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, b->q_scheme.p, (uint32_t)r.qa);
       CU(cudaGetLastError());
       int mgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * 8, (tiles + 15) / 16));
-      CU(cudaMemsetAsync(b->xcount.p, 0, sizeof(ull), st));
+      CU(cudaMemsetAsync(b->xcount.p, 0, 2 * sizeof(ull), st));
       RC(launch_mark(b, P, mgrid, 0));
       launches += 2;
-      ull h_x = 0;
-      CU(cudaMemcpyAsync(&h_x, b->xcount.p, sizeof(ull), cudaMemcpyDeviceToHost, st));
+      ull h_x[2] = {0, 0};
+      CU(cudaMemcpyAsync(h_x, b->xcount.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
-      const uint64_t need = h_x;                // = sum of the bin capacities
-      auto clear_marks = [&]() -> int {
-        // undo the marks: re-walk the marked rows, or wipe the round's slots when that is less traffic
-        if ((uint64_t)tiles * TILE_ROWS * 4 > r.slots * (uint64_t)bitmap_words * 4) {
-          CU(cudaMemsetAsync(b->bitmap.p, 0, r.slots * (size_t)bitmap_words * sizeof(uint32_t), st));
+      const uint64_t need = h_x[0];             // = sum of the bin capacities
+      const uint64_t exact_tiles = h_x[1];      // tiles of exact-scheme lists (their doc bitmaps need clearing)
+      auto clear_marks = [&](bool scored) -> int {
+        // Row masks of the primary scheme are cleared by the scoring pass itself.  The doc bitmaps of
+        // the exact scheme are undone by re-walking the marked rows, or the round's whole pool range
+        // is wiped when that is less traffic (and always when nothing was scored).
+        if (scored && exact_tiles == 0) return PB_OK;
+        if (!scored || exact_tiles * TILE_ROWS * 4 > r.words * 4) {
+          CU(cudaMemsetAsync(b->bitmap.p, 0, (size_t)(r.words + 4) * sizeof(uint32_t), st));
         } else {
           RC(launch_mark(b, P, mgrid, 1));
           ++launches;
@@ -688,7 +720,7 @@ int batch_run(pb_batch* b) {
         return PB_OK;
       };
       if (need > rec_cap) {
-        RC(clear_marks());                      // nothing was scored yet
+        RC(clear_marks(false));                 // nothing was scored yet
         if (r.qb - r.qa > 1) {
           uint64_t mid = r.qa + (r.qb - r.qa) / 2;
           work.push_back(make_round(mid, r.qb));
@@ -731,6 +763,21 @@ int batch_run(pb_batch* b) {
         CU(cudaMemcpyAsync(&h_over, b->counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaMemsetAsync(b->counters.p + 3, 0, sizeof(uint32_t), st));
+        if (std::getenv("PB_DEBUG")) {
+          std::vector<uint32_t> hc(n_bins);
+          CU(cudaMemcpy(hc.data(), b->bin_cursor.p, n_bins * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+          uint64_t hist[8] = {0}; uint64_t big_bins = 0; uint32_t mx = 0; uint64_t mxi = 0;
+          for (uint64_t i = 0; i < n_bins; ++i) { uint32_t c = hc[i]; int k = c == 0 ? 0 : c <= 4 ? 1 : c <= 8 ? 2 : c <= 16 ? 3 : c <= 32 ? 4 : c <= 128 ? 5 : c <= 1024 ? 6 : 7; hist[k] += c; if (c > 32) ++big_bins; if (c > mx) { mx = c; mxi = i; } }
+          uint64_t qq = std::upper_bound(b->h_binoff.begin(), b->h_binoff.end(), b->h_binoff[r.qa] + mxi) - b->h_binoff.begin() - 1;
+          std::vector<uint8_t> hs(Q); std::vector<uint8_t> hsc(Q);
+          CU(cudaMemcpy(hs.data(), b->q_shift.p, Q, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(hsc.data(), b->q_scheme.p, Q, cudaMemcpyDeviceToHost));
+          fprintf(stderr, "[pb] records by bin size 0:%llu <=4:%llu <=8:%llu <=16:%llu <=32:%llu <=128:%llu <=1024:%llu more:%llu | bins>32: %llu | max bin %u (query %llu, bins of query %llu, shift %u scheme %u recbound %llu)\n",
+                  (ull)hist[0], (ull)hist[1], (ull)hist[2], (ull)hist[3], (ull)hist[4], (ull)hist[5], (ull)hist[6], (ull)hist[7], (ull)big_bins, mx, (ull)qq,
+                  (ull)(b->h_binoff[qq + 1] - b->h_binoff[qq]), hs[qq], hsc[qq], (ull)(b->h_recoff[qq + 1] - b->h_recoff[qq]));
+        }
+        if (std::getenv("PB_DEBUG"))
+          fprintf(stderr, "[pb] round q[%llu,%llu) segs %llu tiles %llu bins %llu need %llu overflow %u exact_tiles %llu words %llu\n",
+                  (ull)r.qa, (ull)r.qb, (ull)nseg, (ull)tiles, (ull)n_bins, (ull)need, h_over, (ull)exact_tiles, (ull)r.words);
         if (h_over > legacy_cap) {
           legacy_cap = (uint64_t)h_over + h_over / 4 + 1024;
           CU(b->rec_key.ensure(legacy_cap)); CU(b->rec_val.ensure(legacy_cap));
@@ -755,7 +802,7 @@ int batch_run(pb_batch* b) {
           S.legacy_records += h_over;
         }
       }
-      RC(clear_marks());
+      RC(clear_marks(true));
       CU(cudaMemsetAsync(b->counters.p + 1, 0, sizeof(uint32_t), st));
     }
     S.side_rounds = n_rounds;

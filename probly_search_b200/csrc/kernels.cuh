@@ -32,15 +32,16 @@ constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 #ifndef PB_WINDOW_MAX
 #define PB_WINDOW_MAX 32u      // records a bin-fold window holds; larger bins take the sorted fallback (tests lower it)
 #endif
-#ifndef PB_SCORE_MIN_BLOCKS
-#define PB_SCORE_MIN_BLOCKS 3      // resident CTAs per SM the scoring kernel is compiled for (F <= 2)
-#endif
 
 // How a posting list of a multi-list query is treated by the scoring kernel:
-//   PRIMARY / SECONDARY ("primary scheme", few secondary rows): the secondary lists mark their
-//     docs and are diverted whole; the primary (largest) list diverts only rows whose doc is marked.
+//   PRIMARY / SECONDARY ("primary scheme", few secondary rows): every secondary row is diverted to
+//     the fold; while marking, each secondary doc is looked up in the primary (largest) list by binary
+//     search and, when present, sets that ROW's bit in the query's row mask (1 bit per primary row,
+//     tile-aligned), so the scoring pass learns which primary rows to divert from one coalesced
+//     16-byte load per tile at an address that does not depend on the posting data.
 //   MULTI ("exact scheme", many secondary rows): a marking pass over ALL lists finds the docs hit
-//     by >= 2 (query term, expansion) events; every list diverts exactly those rows.
+//     by >= 2 (query term, expansion) events in per-query doc bitmaps; every list diverts exactly
+//     those rows.
 enum SegMode : uint8_t { MODE_DIRECT = 0, MODE_PRIMARY = 1, MODE_SECONDARY = 2, MODE_MULTI = 3 };
 
 // One posting list walked for one (query term, expanded term): the unit query.rs:38-91 iterates.
@@ -132,10 +133,19 @@ struct ScoreParams {
   const double* tab;             // [F][tfcap][flcap] saturated tf (bm25.rs:78-82), host-computed
   uint32_t tab_tfcap[4], tab_flcap[4], tab_off[4], tab_total;
   uint32_t tab_full;             // the table covers every (tf, fl) present in the index
+  // Shared-memory copy of the table: every entry is replicated 2^tab_rep_shift times, copy c of entry i
+  // at byte (i << tab_rep_shift | c) * 8, and lane l reads copy l & (rep - 1).  With 16 copies the
+  // 16 lanes of an LDS.64 phase always hit 16 different bank pairs: no bank conflicts whatever the
+  // (tf, fl) values are.  tab_stride = 8 << tab_rep_shift bytes, tab_boff[f] = tab_off[f] * tab_stride.
+  uint32_t tab_rep_shift, tab_stride, tab_boff[4];
   uint32_t boosts_all_one;       // every fields_boost is exactly 1.0
   // side path
-  uint32_t* bitmap;              // [slots][bitmap_words]
-  uint32_t bitmap_words;         // words per slot (summary + doc bits)
+  uint32_t* bitmap;              // pool of the round: query q's words start at q_bmoff[q] - round_bm0
+  const unsigned long long* q_bmoff;   // [n_queries + 1] exclusive prefix of the per-query word counts
+  unsigned long long round_bm0;
+  const unsigned long long* q_prim;    // primary scheme: 0xFFFFFFFF - (low word) = segment index of the primary list
+  unsigned long long* xtiles;          // tiles of exact-scheme lists walked by the marking pass (clear heuristic)
+  uint32_t bitmap_words;         // words of an exact-scheme query (summary + two doc bit planes)
   uint32_t bitmap_sum_words;     // leading summary words of a slot
   uint32_t bitmap_doc_words;     // words of one per-doc bit plane (a slot has two)
   unsigned long long* xcount;    // exact-scheme rows the scoring pass will divert (counted while marking)
@@ -163,24 +173,47 @@ struct ScoreParams {
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
+// Posting tiles are streamed once per segment; how they travel is a tuning knob:
+//   PB_LDPOLICY 0: ld.global.nc.L1::no_allocate (pure stream)   1: ld.global.nc (allocates in L1)
+//   PB_PF 0: no prefetch   1: prefetch.global.L1 of a later tile, one 128 B line per lane (20 lanes at F = 2)
+//   PB_PF_DIST: how many tiles ahead
+#ifndef PB_LDPOLICY
+#define PB_LDPOLICY 0
+#endif
+#ifndef PB_PF
+#define PB_PF 0
+#endif
+#ifndef PB_PF_DIST
+#define PB_PF_DIST 1
+#endif
 __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
   uint4 r;
+#if PB_LDPOLICY == 0
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+#else
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+#endif
   return r;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Digest terms (include/probly_b200.h "Digests"): cheap on purpose, they run once per result.
-__device__ __forceinline__ uint32_t doc_mix(uint32_t doc) {
-  uint32_t a = (doc + 1u) * 0x9E3779B1u;
-  return (a ^ (a >> 16)) >> 2;          // 30 bits: four terms add up inside 32 bits
-}
+//   a(d) = (u32)(d + 1) * 0x9E3779B1            doc_digest   += (u64)a * a
+//   y    = lo(s) ^ hi(s) * 0x85EBCA77 ^ a(d)    score_digest += (u64)y * y
+// Each sum is one IMAD.WIDE.U32 into the 64-bit accumulator.
+__device__ __forceinline__ uint32_t doc_mix(uint32_t doc) { return (doc + 1u) * 0x9E3779B1u; }
 __device__ __forceinline__ uint32_t score_mix(uint32_t a, double s) {
   uint32_t lo = (uint32_t)__double2loint(s), hi = (uint32_t)__double2hiint(s);
-  uint32_t y = lo ^ (hi * 0x85EBCA77u) ^ a;
-  return (y ^ (y >> 15)) >> 2;
+  return lo ^ (hi * 0x85EBCA77u) ^ a;
 }
+__device__ __forceinline__ uint64_t sq64(uint32_t v) { return (uint64_t)v * v; }
 
 __device__ __forceinline__ bool better(double as, uint32_t ad, double bs, uint32_t bd) {
   return as > bs || (as == bs && ad < bd);     // (score desc, doc asc), src/lib.rs:54-58
@@ -261,8 +294,8 @@ struct WarpAcc {
     if (valid) {
       ++cnt;
       uint32_t a = doc_mix(doc);
-      dd += a;
-      sd += score_mix(a, s);
+      dd += sq64(a);
+      sd += sq64(score_mix(a, s));
     }
     if (o.full_q) capture(o, valid, doc, s, lane);
     if (o.k) insert_candidates(valid && better(s, doc, thr_s, thr_d), doc, s, lane, (int)o.k);
@@ -277,24 +310,26 @@ struct WarpAcc {
     bool hit = false;
     if (__all_sync(0xffffffffu, some == 0xFu)) {            // the common case: every row produced a result
       cnt += 4;
-      uint32_t a[4], y[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { a[j] = doc_mix(doc[j]); y[j] = score_mix(a[j], sc[j]); hit |= sc[j] >= thr_s; }
-      dd += (a[0] + a[1]) + (a[2] + a[3]);
-      sd += (y[0] + y[1]) + (y[2] + y[3]);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t a = doc_mix(doc[j]);
+        dd += sq64(a);
+        sd += sq64(score_mix(a, sc[j]));
+      }
+      // Some(score) is > 0 (bm25.rs:89) or >= +0 (zero_to_one): positive doubles order like their high
+      // words, so "some score may reach the k-th best" is one integer compare (a superset; exact test below)
+      const int hmax = max(max(__double2hiint(sc[0]), __double2hiint(sc[1])), max(__double2hiint(sc[2]), __double2hiint(sc[3])));
+      hit = hmax >= __double2hiint(thr_s);
     } else {
       cnt += __popc(some);
-      uint32_t sa = 0, sy = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t m = 0u - ((some >> j) & 1u);          // all ones when the row produced a result
         const uint32_t a = doc_mix(doc[j]);
-        sa += a & m;
-        sy += score_mix(a, sc[j]) & m;
+        dd += sq64(a & m);
+        sd += sq64(score_mix(a, sc[j]) & m);
         hit |= (m != 0u) && (sc[j] >= thr_s);
       }
-      dd += sa;
-      sd += sy;
     }
     if (CAPTURE && o.full_q) {
 #pragma unroll
@@ -553,12 +588,13 @@ __global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const uns
                                 uint8_t* __restrict__ q_scheme, uint8_t* __restrict__ q_shift,
                                 const uint64_t* __restrict__ query_term_off,
                                 const unsigned long long* __restrict__ qt_goff,
-                                unsigned long long* __restrict__ q_gsegoff) {
+                                unsigned long long* __restrict__ q_gsegoff, unsigned long long* __restrict__ q_bmwords,
+                                uint32_t bitmap_words) {
   uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (q > n_queries) return;
   q_gsegoff[q] = qt_goff[query_term_off[q]];   // qt_goff has n_qterms + 1 entries
   if (q == n_queries) return;
-  unsigned long long bound = 0, nbins = 0;
+  unsigned long long bound = 0, nbins = 0, bmw = 0;
   uint8_t scheme = 0, shift = 0;
   if (q_isg[q]) {
     unsigned long long p = q_prim[q];
@@ -569,10 +605,14 @@ __global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const uns
       // exact scheme: the record count is only known after the marking pass; plan with an estimate
       scheme = 1;
       bound = rows / 2 + 1024;
+      bmw = bitmap_words;
     } else {
       // primary scheme: every secondary row + at most one primary row per secondary doc
       seg_g[idx].mode = MODE_PRIMARY;
       bound = 2ull * secondary;
+      // row mask: 4 words per tile the primary list touches
+      const unsigned long long a = seg_g[idx].row_begin, e = a + seg_g[idx].n_rows;
+      bmw = 4ull * ((e + TILE_ROWS - 1) / TILE_ROWS - a / TILE_ROWS) + 4ull;
     }
     // doc-range bins of width 2^shift sized for ~8 records each (a warp window holds 32)
     const unsigned long long n_docs_pow = 1ull << doc_bits;
@@ -583,6 +623,7 @@ __global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const uns
     nbins = (n_docs_pow >> sh);
   }
   q_recbound[q] = bound;
+  q_bmwords[q] = bmw;
   q_nbins[q] = nbins;
   q_scheme[q] = scheme;
   q_shift[q] = shift;
@@ -612,11 +653,15 @@ __device__ __forceinline__ uint32_t seg_of_tile(const uint64_t* __restrict__ til
   return a;
 }
 
-// Marking pass of a side-path round (clear = 1 undoes it afterwards).  Slot layout of a query:
-//   [summary: 1 bit per 1024 docs][bits A: 1 bit per doc][bits B: 1 bit per doc]
-// primary scheme: SECONDARY lists set A (= "diverted docs") and the summary.
-// exact scheme:   every list sets A (= "seen"); a doc seen again sets B (= "multi") and the
-//                 summary, and the exact number of rows the scoring pass will divert is counted.
+// Marking pass of a side-path round.
+// exact scheme (MODE_MULTI), words of the query = [summary: 1 bit per 1024 docs][bits A: 1 bit per doc]
+//   [bits B: 1 bit per doc]: every list sets A (= "seen"); a doc seen again sets B (= "multi") and the
+//   summary.  clear = 1 undoes the marks afterwards.
+// primary scheme (MODE_SECONDARY rows), words of the query = row mask of the PRIMARY list, 4 words per
+//   tile: each secondary doc is searched in the primary list (docs ascend inside a list) and, when
+//   present, sets the bit of that primary row.  The scoring pass clears the words it consumes.
+// Both count, per doc-range bin, the records the scoring pass will write (the row itself, + 1 for the
+// doc's primary / first row, counted once).
 template <int F>
 __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant__ ScoreParams P, int clear) {
   const int lane = threadIdx.x & 31;
@@ -627,50 +672,77 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
   const uint64_t t1 = P.tile_begin + (T * (w + 1)) / W;
   if (t >= t1) return;
   uint32_t s = seg_of_tile(P.tile_off, P.seg_begin, P.seg_end, t);
-  unsigned long long xcount = 0;
+  unsigned long long xcount = 0, xtiles = 0;
   while (t < t1) {
     const Seg sg = P.segs[s];
     const uint64_t st0 = P.tile_off[s], st1 = P.tile_off[s + 1];
     const uint64_t tend = min(t1, st1);
-    if (sg.mode == MODE_SECONDARY || sg.mode == MODE_MULTI) {
-      uint32_t* sm = P.bitmap + (size_t)sg.slot * P.bitmap_words;
+    const bool exact = sg.mode == MODE_MULTI;
+    if (tend > t && (exact || (sg.mode == MODE_SECONDARY && !clear))) {
+      uint32_t* sm = P.bitmap + (size_t)(P.q_bmoff[sg.q] - P.round_bm0);
       uint32_t* ba = sm + P.bitmap_sum_words;
       uint32_t* bb = ba + P.bitmap_doc_words;
-      const bool exact = sg.mode == MODE_MULTI;
       const uint32_t bin_base = (uint32_t)(P.q_binoff[sg.q] - P.round_bin0);
       const uint32_t shift = P.q_shift[sg.q];
       const uint64_t abs0 = sg.row_begin / TILE_ROWS;
       const uint64_t rend = sg.row_begin + sg.n_rows;
+      uint64_t pbeg = 0, pend = 0, pabs0 = 0;
+      if (!exact) {
+        const Seg pr = P.segs[0xFFFFFFFFu - (uint32_t)(P.q_prim[sg.q] & 0xFFFFFFFFull)];
+        pbeg = pr.row_begin; pend = pbeg + pr.n_rows; pabs0 = pbeg / TILE_ROWS;
+      }
+      if (exact) xtiles += tend - t;
       for (; t < tend; ++t) {
         uint64_t row0 = (abs0 + (t - st0)) * TILE_ROWS + lane * 4;
         uint4 d = ldg_stream(P.ix.post_blocks + (abs0 + (t - st0)) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 4);
         uint32_t dv[4] = {d.x, d.y, d.z, d.w};
+        bool inr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint64_t row = row0 + j;
-          if (row >= sg.row_begin && row < rend) {
+        for (int j = 0; j < 4; ++j) inr[j] = row0 + j >= sg.row_begin && row0 + j < rend;
+        if (exact) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!inr[j]) continue;
             const uint32_t doc = dv[j], bit = 1u << (doc & 31);
             if (clear) {
-              ba[doc >> 5] = 0u; sm[doc >> 15] = 0u;
-              if (exact) bb[doc >> 5] = 0u;
-            } else {
-              // inc = records the scoring pass may write for this row's doc because of this row:
-              // the row itself (+ one more for the doc's first / primary row, counted once)
-              uint32_t inc = 0;
-              if (!exact) {
-                const uint32_t old = atomicOr(&ba[doc >> 5], bit);
-                atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
-                inc = (old & bit) ? 1u : 2u;
-              } else if (atomicOr(&ba[doc >> 5], bit) & bit) {    // seen before: a multi-event doc
-                const uint32_t old = atomicOr(&bb[doc >> 5], bit);
-                atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
-                inc = (old & bit) ? 1u : 2u;
-              }
-              if (inc) {
-                atomicAdd(&P.bin_count[bin_base + (doc >> shift)], inc);
-                xcount += inc;
+              ba[doc >> 5] = 0u; sm[doc >> 15] = 0u; bb[doc >> 5] = 0u;
+            } else if (atomicOr(&ba[doc >> 5], bit) & bit) {      // seen before: a multi-event doc
+              const uint32_t old = atomicOr(&bb[doc >> 5], bit);
+              atomicOr(&sm[doc >> 15], 1u << ((doc >> 10) & 31));
+              const uint32_t inc = (old & bit) ? 1u : 2u;
+              atomicAdd(&P.bin_count[bin_base + (doc >> shift)], inc);
+              xcount += inc;
+            }
+          }
+        } else {
+          // four lower-bound searches of the lane's docs in the primary list, in lockstep
+          uint64_t lo[4], hi[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { lo[j] = pbeg; hi[j] = inr[j] ? pend : pbeg; }
+          while (true) {
+            bool more = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (lo[j] < hi[j]) {
+                const uint64_t mid = (lo[j] + hi[j]) >> 1;
+                if (row_doc<F>(P.ix.post_blocks, mid) < dv[j]) lo[j] = mid + 1; else hi[j] = mid;
+                more = true;
               }
             }
+            if (!more) break;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!inr[j]) continue;
+            uint32_t inc = 1u;
+            const uint64_t r = lo[j];
+            if (r < pend && row_doc<F>(P.ix.post_blocks, r) == dv[j]) {
+              const uint32_t bit = 1u << (r & 31);
+              const uint32_t old = atomicOr(&sm[(r / TILE_ROWS - pabs0) * 4 + ((r % TILE_ROWS) >> 5)], bit);
+              inc = (old & bit) ? 1u : 2u;
+            }
+            atomicAdd(&P.bin_count[bin_base + (dv[j] >> shift)], inc);
+            xcount += inc;
           }
         }
       }
@@ -678,8 +750,9 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
     t = tend;
     ++s;
   }
-  xcount = warp_sum_u64(xcount);
+  xcount = warp_sum_u64(xcount);     // xtiles is warp-uniform already
   if (lane == 0 && xcount) atomicAdd(P.xcount, xcount);     // = sum of all bin capacities of the round
+  if (lane == 0 && xtiles && !clear) atomicAdd(P.xtiles, xtiles);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -693,21 +766,27 @@ __device__ __forceinline__ uint32_t u4c(const uint4& v, int j) { return j == 0 ?
 // TABFULL: every (tf, fl) of the index is inside the shared-memory table of tf' (no range check,
 // no division in the loop).  SIMPLE: all boosts and the expansion boost are exactly 1.0, so the
 // two multiplications by 1.0 (exact identities) are skipped.
-template <int F, bool TABFULL, bool SIMPLE>
-__device__ __forceinline__ void bm25_rows(const ScoreParams& P, const double* __restrict__ s_tab, const uint4 (&tq)[F],
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+template <int F, bool TABFULL, int SIMPLE>
+__device__ __forceinline__ void bm25_rows(const ScoreParams& P, const uint32_t tbase, const uint4 (&tq)[F],
                                           const uint4 (&lq)[F], double idf, double ebst, double (&sc)[4]) {
 #pragma unroll
   for (int f = 0; f < F; ++f) {
-    const double* tab = s_tab + P.tab_off[f];
+    const uint32_t fbase = tbase + P.tab_boff[f];     // this lane's copy of field f's table (shared address)
     const uint32_t flcap = P.tab_flcap[f];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t tf = u4c(tq[f], j), fl = u4c(lq[f], j);
       double tfn;
-      if (TABFULL) tfn = tab[tf * flcap + fl];
-      else tfn = (tf < P.tab_tfcap[f] && fl < flcap) ? tab[tf * flcap + fl] : bm25_tf_slow(P, tf, fl, f);
+      if (TABFULL) tfn = lds_f64(fbase + (tf * flcap + fl) * P.tab_stride);
+      else tfn = (tf < P.tab_tfcap[f] && fl < flcap) ? lds_f64(fbase + (tf * flcap + fl) * P.tab_stride) : bm25_tf_slow(P, tf, fl, f);
       double c = __dmul_rn(tfn, idf);
-      if (!SIMPLE) c = __dmul_rn(__dmul_rn(c, P.boost[f]), ebst);
+      if (SIMPLE == 0) c = __dmul_rn(c, P.boost[f]);     // x * 1.0 == x exactly, so levels 1 / 2 may skip
+      if (SIMPLE < 2) c = __dmul_rn(c, ebst);
       if (TABFULL) {
         // table rows for tf = 0 hold +0.0 and idf / boosts / eb are finite, so c = +-0.0 there and
         // adding it is an exact identity: no select needed (the reference skips tf = 0, bm25.rs:73)
@@ -773,8 +852,9 @@ struct SegCtx {
   uint32_t seg;             // segment index (event order key of the side path)
   uint32_t slot;
   uint32_t mode;
-  const uint32_t* sum;      // GMODE: the query's summary bits / doc bits
+  const uint32_t* sum;      // GMODE exact scheme: the query's summary bits / "multi" doc bits
   const uint32_t* bm;
+  uint32_t* rowmask;        // GMODE primary scheme: row mask word of the segment's first tile
   uint32_t bin_base;        // GMODE: first bin of the query, relative to the round
   uint32_t shift;           // GMODE: log2(bin width in docs)
 };
@@ -786,11 +866,19 @@ template <int F>
 struct TileRegs {
   uint4 dq;
   uint4 tq[F], lq[F];
+  uint32_t mw;      // GMODE primary list: the row-mask word holding this lane's 4 bits
 };
-template <int F>
-__device__ __forceinline__ void load_tile(const ScoreParams& P, uint64_t tile_row, int lane, TileRegs<F>& R) {
+template <int F, bool GMODE>
+__device__ __forceinline__ void load_tile(const ScoreParams& P, const SegCtx& C, uint64_t tile_row, int lane, TileRegs<F>& R) {
   // one contiguous (1 + 2F) x 512 B block per tile: a single base address, immediate column offsets
   const uint32_t* base = P.ix.post_blocks + (tile_row / TILE_ROWS) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 4;
+  R.mw = 0;
+  if (GMODE && C.mode == MODE_PRIMARY) {
+    // address known before any posting data arrives: travels together with the tile
+    uint32_t* wp = C.rowmask + (tile_row / TILE_ROWS - C.rbeg / TILE_ROWS) * 4 + (lane >> 3);
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(R.mw) : "l"(wp));
+    if (R.mw != 0u && (lane & 7) == 0) *wp = 0u;      // consumed: the pool is clean again for the next round
+  }
   R.dq = ldg_stream(base);
 #pragma unroll
   for (int f = 0; f < F; ++f) {
@@ -799,8 +887,8 @@ __device__ __forceinline__ void load_tile(const ScoreParams& P, uint64_t tile_ro
   }
 }
 
-template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, bool SIMPLE>
-__device__ __forceinline__ void compute_tile(const ScoreParams& P, const double* __restrict__ s_tab, const SegCtx& C,
+template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE>
+__device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                              const TileRegs<F>& R, uint64_t tile_row, int lane, WarpAcc& acc,
                                              uint32_t& st_div) {
   const uint64_t row0 = tile_row + lane * 4;
@@ -828,11 +916,21 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const double*
   uint32_t some = valid;
   if (SCORER == 0) {
     if (FAST) bm25_rows<F, true, SIMPLE>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
-    else if (P.tab_full) bm25_rows<F, true, false>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
-    else bm25_rows<F, false, false>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
+    else if (P.tab_full) bm25_rows<F, true, 0>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
+    else bm25_rows<F, false, 0>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
+    // Some(score) only if score > 0 (bm25.rs:89-92).  A double whose high word, read as a signed
+    // integer, lies in (0, 0x7FF00000) is a positive finite number: when that holds for the four
+    // rows of the lane (two integer min/max) the per-row f64 compares are skipped.
+    bool check = true;
+    if (FAST) {
+      const int h0 = __double2hiint(sc[0]), h1 = __double2hiint(sc[1]), h2 = __double2hiint(sc[2]), h3 = __double2hiint(sc[3]);
+      check = !(min(min(h0, h1), min(h2, h3)) > 0 && max(max(h0, h1), max(h2, h3)) < 0x7FF00000);
+    }
+    if (check) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (!(sc[j] > 0.0)) some &= ~(1u << j);      // Some(score) only if score > 0 (bm25.rs:89-92)
+      for (int j = 0; j < 4; ++j)
+        if (!(sc[j] > 0.0)) some &= ~(1u << j);
+    }
   } else {
     z2o_rows<F>(tq, lq, C.zs, C.qtl, sc);
   }
@@ -841,7 +939,9 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const double*
     // (scored or not: a None still marks the doc visited, query.rs:87), and the rows of the
     // primary list whose doc also occurs in a secondary list
     uint32_t dmask = valid;
-    if (C.mode != MODE_SECONDARY) {
+    if (C.mode == MODE_PRIMARY) {
+      dmask = (R.mw >> ((lane & 7) * 4)) & valid;
+    } else if (C.mode != MODE_SECONDARY) {
       dmask = 0;
       bool maybe = true;
       if (!EDGE) {
@@ -887,106 +987,52 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const double*
   else acc.template add4<true>(P.out, some, dv, sc, lane);
 }
 
-template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, bool SIMPLE>
-__device__ __forceinline__ void process_tile(const ScoreParams& P, const double* __restrict__ s_tab, const SegCtx& C,
+template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE>
+__device__ __forceinline__ void process_tile(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                              uint64_t tile_row, int lane, WarpAcc& acc, uint32_t& st_div) {
   TileRegs<F> R;
-  load_tile<F>(P, tile_row, lane, R);
+  load_tile<F, GMODE>(P, C, tile_row, lane, R);
   compute_tile<F, SCORER, GMODE, EDGE, FAST, SIMPLE>(P, s_tab, C, R, tile_row, lane, acc, st_div);
 }
 
-// Interior tiles [t, ib) of one segment, software-pipelined: the loads of tile i+1 are in flight
-// while tile i is scored (PB_PREFETCH), so a warp never sits idle on its own L2/HBM latency.
-#ifndef PB_PREFETCH
-#define PB_PREFETCH 0
-#endif
-template <int F, int SCORER, bool GMODE, bool FAST, bool SIMPLE>
-__device__ __forceinline__ void interior_tiles(const ScoreParams& P, const double* __restrict__ s_tab, const SegCtx& C,
+// Interior tiles of one segment (every row belongs to the segment).
+template <int F, int SCORER, bool GMODE, bool FAST, int SIMPLE>
+__device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                                uint64_t tile_row, uint32_t n_tiles, int lane, WarpAcc& acc,
                                                uint32_t& st_div) {
-#if PB_PREFETCH
-  if (n_tiles == 0) return;
-  TileRegs<F> cur;
-  load_tile<F>(P, tile_row, lane, cur);
   for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS) {
-    TileRegs<F> nxt;
-    // the spare tile at the end of every column makes this load safe even past the last tile
-    load_tile<F>(P, tile_row + TILE_ROWS, lane, nxt);
-    compute_tile<F, SCORER, GMODE, false, FAST, SIMPLE>(P, s_tab, C, cur, tile_row, lane, acc, st_div);
-    cur = nxt;
-  }
+#if PB_PF
+    // pull a later tile of this list towards the SM while this one is scored: a tile is one contiguous
+    // block of (1 + 2F) x 512 B = 4 (1 + 2F) lines, one line per lane
+    if (i + PB_PF_DIST < n_tiles && lane < 4 * (1 + 2 * F)) {
+      const uint32_t* nb = P.ix.post_blocks + (tile_row / TILE_ROWS + PB_PF_DIST) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 32;
+#if PB_PF == 1
+      prefetch_l1(nb);
 #else
-  for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS)
+      prefetch_l2(nb);
+#endif
+    }
+#endif
     process_tile<F, SCORER, GMODE, false, FAST, SIMPLE>(P, s_tab, C, tile_row, lane, acc, st_div);
-#endif
+  }
 }
 
-// ------------------------------------------------------------------------------------------
-// TMA staging.  Every warp runs its own PB_STAGES-deep ring of tiles in shared memory: a tile
-// is ONE contiguous block of (1 + 2F) x 512 B in the tile-blocked layout, fetched with a single
-// cp.async.bulk (1-D TMA) that lands on a per-stage mbarrier; the warp then reads its 4 rows per
-// column with one conflict-free LDS.128 per lane.  Loads in flight cost no registers, so the
-// latency of L2/HBM is hidden by the ring depth instead of by occupancy.
-// ------------------------------------------------------------------------------------------
-#ifndef PB_TMA
-#define PB_TMA 0
-#endif
-#ifndef PB_STAGES
-#define PB_STAGES 3
-#endif
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-template <int F>
-struct TileRing {
-  static constexpr int NCOL = 1 + 2 * F;
-  static constexpr int COL_BYTES = TILE_ROWS * 4;
-  static constexpr int STAGE_BYTES = NCOL * COL_BYTES;
-  static constexpr int WARP_BYTES = (PB_STAGES * STAGE_BYTES + PB_STAGES * 8 + 127) / 128 * 128;   // + mbarriers
-};
+// CTA shape of the scoring kernel: no barrier after the table is loaded, so a CTA is just a bag of
+// warps.  The host picks (threads per CTA, CTAs per SM) so that ~24 warps are resident per SM
+// whatever the shared-memory table costs: 3 x 256, 2 x 384 or 1 x 768 threads.
+constexpr int SCORE_MAX_THREADS = 768;
 
 template <int F, int SCORER, bool GMODE>
-__global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? PB_SCORE_MIN_BLOCKS : 2)) score_kernel(const __grid_constant__ ScoreParams P) {
+__global__ void __launch_bounds__(SCORE_MAX_THREADS, 1) score_kernel(const __grid_constant__ ScoreParams P) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  double* s_tab = reinterpret_cast<double*>(s_raw);
   if (SCORER == 0) {
-    for (uint32_t i = threadIdx.x; i < P.tab_total; i += blockDim.x) s_tab[i] = P.tab[i];
+    double* st = reinterpret_cast<double*>(s_raw);
+    const uint32_t n = P.tab_total << P.tab_rep_shift;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) st[i] = P.tab[i >> P.tab_rep_shift];
   }
   const int lane = threadIdx.x & 31;
-  const int wid = threadIdx.x >> 5;
-#if PB_TMA
-  using Ring = TileRing<F>;
-  // ring of this warp: stages, then the stage mbarriers
-  unsigned char* ring = s_raw + ((P.tab_total * 8 + 127) & ~127u) + (size_t)wid * Ring::WARP_BYTES;
-  const uint32_t ring_s = smem_u32(ring);
-  const uint32_t bar_s = ring_s + PB_STAGES * Ring::STAGE_BYTES;
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < PB_STAGES; ++i) mbar_init(bar_s + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-#endif
+  // shared address of this lane's copy of table entry 0
+  const uint32_t s_tab = smem_u32(s_raw) + ((uint32_t)lane & ((1u << P.tab_rep_shift) - 1u)) * 8u;
   __syncthreads();
   const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1003,36 +1049,6 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? PB_SCORE_MIN_BLOCKS : 2
   uint32_t st_div = 0;
   // launch-wide: may the interior tiles take the check-free path?
   const bool fast = !P.ix.has_removed && P.out.full_q == nullptr && (SCORER != 0 || P.tab_full);
-
-#if PB_TMA
-  // producer cursor: the next tile to fetch (runs PB_STAGES - 1 tiles ahead of the consumer)
-  uint64_t tp = span0;
-  uint32_t sp = s;
-  uint64_t sp_st0 = P.tile_off[sp], sp_st1 = P.tile_off[sp + 1];
-  uint64_t sp_abs0 = P.segs[sp].row_begin / TILE_ROWS;
-  uint32_t n_issued = 0, n_consumed = 0;
-  auto issue = [&]() {
-    while (tp >= sp_st1) {                    // next segment that owns tiles
-      ++sp;
-      sp_st0 = sp_st1;
-      sp_st1 = P.tile_off[sp + 1];
-      sp_abs0 = P.segs[sp].row_begin / TILE_ROWS;
-    }
-    const uint64_t tile_row = (sp_abs0 + (tp - sp_st0)) * TILE_ROWS;
-    const uint32_t stage = n_issued % PB_STAGES;
-    const uint32_t bar = bar_s + 8 * stage;
-    if (lane == 0) {
-      mbar_expect_tx(bar, Ring::STAGE_BYTES);
-      tma_load_1d(ring_s + stage * Ring::STAGE_BYTES,
-                  P.ix.post_blocks + (tile_row / TILE_ROWS) * (uint64_t)(Ring::NCOL * TILE_ROWS), Ring::STAGE_BYTES, bar);
-    }
-    ++tp;
-    ++n_issued;
-  };
-#pragma unroll 1
-  for (int i = 0; i < PB_STAGES - 1; ++i)
-    if (tp < span1) issue();
-#endif
 
   while (t < span1) {
     const Seg sg = P.segs[s];
@@ -1061,57 +1077,35 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? PB_SCORE_MIN_BLOCKS : 2
         C.qtl = (uint32_t)(P.query_term_off[sg.q + 1] - P.query_term_off[sg.q]);
       }
       C.bin_base = 0; C.shift = 0;
+      C.rowmask = nullptr;
       if (GMODE) {
-        C.sum = P.bitmap + (size_t)sg.slot * P.bitmap_words;
-        C.bm = C.sum + P.bitmap_sum_words + (sg.mode == MODE_MULTI ? P.bitmap_doc_words : 0u);
+        C.rowmask = P.bitmap + (size_t)(P.q_bmoff[sg.q] - P.round_bm0);
+        C.sum = C.rowmask;
+        C.bm = C.sum + P.bitmap_sum_words + P.bitmap_doc_words;      // exact scheme: the "multi" plane
         C.bin_base = (uint32_t)(P.q_binoff[sg.q] - P.round_bin0);
         C.shift = P.q_shift[sg.q];
       }
       const uint64_t abs0 = C.rbeg / TILE_ROWS;
-#if PB_TMA
-      uint64_t tile_row = (abs0 + (t - st0)) * TILE_ROWS;
-      for (; t < tend; ++t, tile_row += TILE_ROWS) {
-        // keep the ring full: fetch the tile PB_STAGES - 1 ahead (its stage was drained last iteration)
-        if (tp < span1) issue();
-        const uint32_t stage = n_consumed % PB_STAGES;
-        mbar_wait(bar_s + 8 * stage, (n_consumed / PB_STAGES) & 1u);
-        ++n_consumed;
-        TileRegs<F> R;
-        const unsigned char* sb = ring + stage * Ring::STAGE_BYTES + lane * 16;
-        R.dq = *reinterpret_cast<const uint4*>(sb);
-#pragma unroll
-        for (int f = 0; f < F; ++f) {
-          R.tq[f] = *reinterpret_cast<const uint4*>(sb + (1 + f) * Ring::COL_BYTES);
-          R.lq[f] = *reinterpret_cast<const uint4*>(sb + (1 + F + f) * Ring::COL_BYTES);
-        }
-        const bool edge = tile_row < C.rbeg || tile_row + TILE_ROWS > C.rend;
-        if (edge) compute_tile<F, SCORER, GMODE, true, false, false>(P, s_tab, C, R, tile_row, lane, acc, st_div);
-        else if (!fast) compute_tile<F, SCORER, GMODE, false, false, false>(P, s_tab, C, R, tile_row, lane, acc, st_div);
-        else if (simple) compute_tile<F, SCORER, GMODE, false, true, true>(P, s_tab, C, R, tile_row, lane, acc, st_div);
-        else compute_tile<F, SCORER, GMODE, false, true, false>(P, s_tab, C, R, tile_row, lane, acc, st_div);
-        __syncwarp();     // every lane has consumed its registers of this stage before it is refilled
-      }
-#else
       // virtual tile range of the segment's fully covered (interior) tiles
       const uint64_t int0 = st0 + ((C.rbeg % TILE_ROWS) ? 1 : 0);
       const uint64_t int1 = st1 - ((C.rend % TILE_ROWS) ? 1 : 0);     // may be < int0 for a tiny segment
       const uint64_t ia = min(max(t, int0), tend), ib = max(min(tend, int1), ia);
       for (; t < ia; ++t)
-        process_tile<F, SCORER, GMODE, true, false, false>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
+        process_tile<F, SCORER, GMODE, true, false, 0>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
       {
         const uint64_t row = (abs0 + (t - st0)) * TILE_ROWS;
         const uint32_t n = (uint32_t)(ib - t);
         if (fast) {
-          if (simple) interior_tiles<F, SCORER, GMODE, true, true>(P, s_tab, C, row, n, lane, acc, st_div);
-          else interior_tiles<F, SCORER, GMODE, true, false>(P, s_tab, C, row, n, lane, acc, st_div);
+          if (simple) interior_tiles<F, SCORER, GMODE, true, 2>(P, s_tab, C, row, n, lane, acc, st_div);
+          else if (P.boosts_all_one) interior_tiles<F, SCORER, GMODE, true, 1>(P, s_tab, C, row, n, lane, acc, st_div);
+          else interior_tiles<F, SCORER, GMODE, true, 0>(P, s_tab, C, row, n, lane, acc, st_div);
         } else {
-          interior_tiles<F, SCORER, GMODE, false, false>(P, s_tab, C, row, n, lane, acc, st_div);
+          interior_tiles<F, SCORER, GMODE, false, 0>(P, s_tab, C, row, n, lane, acc, st_div);
         }
         t = ib;
       }
       for (; t < tend; ++t)
-        process_tile<F, SCORER, GMODE, true, false, false>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
-#endif
+        process_tile<F, SCORER, GMODE, true, false, 0>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
     }
     ++s;
   }
@@ -1120,16 +1114,6 @@ __global__ void __launch_bounds__(CTA_THREADS, (F <= 2 ? PB_SCORE_MIN_BLOCKS : 2
     unsigned long long d = warp_sum_u64(st_div);
     if (lane == 0 && d) atomicAdd(&P.stats[ST_ROWS_DIVERTED], d);
   }
-}
-
-// dynamic shared memory of the scoring kernel: BM25 table + the warps' tile rings
-template <int F>
-inline size_t score_smem_bytes(uint32_t tab_total) {
-  size_t b = ((size_t)tab_total * 8 + 127) & ~(size_t)127;
-#if PB_TMA
-  b += (size_t)WARPS_PER_CTA * TileRing<F>::WARP_BYTES;
-#endif
-  return b;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -32,6 +32,14 @@ struct SplitMix64 {
   uint64_t below(uint64_t n) { return (uint64_t)(uniform() * (double)n); }   // n << 2^53
 };
 
+// Seed of document d's private stream: the doc index goes through the SplitMix64 finaliser first.
+// (Seeding with seed + gamma * d would make doc d + 1's stream doc d's stream shifted by one draw:
+// neighbouring documents would share all but one token.)
+static inline uint64_t doc_stream_seed(uint64_t seed, uint64_t d) {
+  SplitMix64 h(seed ^ (0xD1B54A32D192ED03ULL * (d + 1)));
+  return h.next();
+}
+
 struct Workload {
   uint64_t seed;
   uint32_t V, F;
@@ -96,7 +104,7 @@ void wl_gen_docs(void* h, uint64_t d0, uint64_t d1, uint8_t* tok_bytes, uint64_t
   uint64_t t = 0, b = 0;
   tok_off[0] = 0;
   for (uint64_t d = d0; d < d1; ++d) {
-    SplitMix64 r(w->seed + 0x9E3779B97F4A7C15ULL * (d + 1));
+    SplitMix64 r(doc_stream_seed(w->seed, d));
     r.next();
     for (uint32_t f = 0; f < w->F; ++f) {
       uint32_t n = w->len_min[f] + (uint32_t)r.below(w->len_max[f] - w->len_min[f] + 1);
@@ -148,7 +156,7 @@ void wl_gen_bench_docs(uint64_t seed, uint64_t d0, uint64_t d1, uint8_t* tok_byt
   uint64_t t = 0, b = 0;
   tok_off[0] = 0;
   for (uint64_t d = d0; d < d1; ++d) {
-    SplitMix64 r(seed + 0x9E3779B97F4A7C15ULL * (d + 1));
+    SplitMix64 r(doc_stream_seed(seed, d));
     r.next();
     field_tok_count[d - d0] = 2;
     for (int wd = 0; wd < 2; ++wd) {

@@ -67,7 +67,7 @@ def test_cfg1_full_size(corpus):
     # single-list queries: the result count is the term's posting count
     df = None
     im = ix.flatten()
-    assert int(im.n_rows) == 25_874_361 and int(im.n_terms) == 137_605   # the corpus is the one DESIGN.md describes
+    assert int(im.n_rows) == 25_849_058 and int(im.n_terms) == 262_135   # the corpus is the one DESIGN.md describes
 
 
 def test_cfg2_prefix_zero_to_one_full_corpus(corpus):
