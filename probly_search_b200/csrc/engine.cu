@@ -106,6 +106,8 @@ struct pb_index {
   uint32_t F = 1;
   uint64_t n_nodes = 0, n_edges = 0, n_terms = 0, n_rows = 0, n_rows_padded = 0, n_docs = 0;
   uint32_t max_term_bytes = 0, max_tf[4] = {0, 0, 0, 0}, max_fl[4] = {0, 0, 0, 0};
+  bool narrow = false;          // device posting columns hold one u16 (tf, fl) code per field (see IndexView)
+  uint32_t tile_words = 0, fl_bits[4] = {0, 0, 0, 0};
   DBuf<uint32_t> node_edge_begin, node_term_lo, node_term_hi, edge_char, edge_child;
   DBuf<uint64_t> term_row_begin;
   DBuf<uint32_t> term_byte_len, post_blocks, removed, live_prefix, term_live_rows;
@@ -124,7 +126,8 @@ struct pb_index {
     v.node_edge_begin = node_edge_begin.p; v.node_term_lo = node_term_lo.p; v.node_term_hi = node_term_hi.p;
     v.edge_char = edge_char.p; v.edge_child = edge_child.p;
     v.term_row_begin = term_row_begin.p; v.term_byte_len = term_byte_len.p;
-    v.post_blocks = post_blocks.p;
+    v.post_blocks = post_blocks.p; v.tile_words = tile_words; v.narrow = narrow ? 1u : 0u;
+    for (int f = 0; f < 4; ++f) v.fl_bits[f] = fl_bits[f];
     v.removed = removed.p;
     v.term_df_live = term_df_live.p; v.term_live_rows = term_live_rows.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
     v.term_idf = term_idf.p; v.eb = eb.p;
@@ -284,17 +287,21 @@ double bm25_tf_host(double k1, double b, double avg, uint32_t tf, uint32_t fl) {
 
 int batch_build_table(pb_batch* b) {
   pb_index* ix = b->ix;
+  // (tf, fl) -> saturated tf, per field, tf-major with row stride flc.  In the narrow layout the row
+  // stride is 1 << fl_bits so that a posting code indexes the table directly; the table may then only
+  // be cut along tf.
   uint32_t tfc[4], flc[4];
   for (uint32_t f = 0; f < ix->F; ++f) {
-    tfc[f] = std::min<uint32_t>(ix->max_tf[f] + 1, 64);
-    flc[f] = std::min<uint32_t>(ix->max_fl[f] + 1, 1024);
+    tfc[f] = std::min<uint32_t>(ix->max_tf[f] + 1, ix->narrow ? 65536u : 64u);
+    flc[f] = ix->narrow ? (1u << ix->fl_bits[f]) : std::min<uint32_t>(ix->max_fl[f] + 1, 1024);
   }
   auto total = [&]() { uint64_t t = 0; for (uint32_t f = 0; f < ix->F; ++f) t += (uint64_t)tfc[f] * flc[f]; return t; };
-  while (total() > 4096) {     // 32 KB of shared memory
+  while (total() > 8192) {     // 64 KB of shared memory
     uint32_t best = 0;
     for (uint32_t f = 1; f < ix->F; ++f) if ((uint64_t)tfc[f] * flc[f] > (uint64_t)tfc[best] * flc[best]) best = f;
     if (tfc[best] > 4) tfc[best] = (tfc[best] + 1) / 2;
-    else if (flc[best] > 2) flc[best] = (flc[best] + 1) / 2;
+    else if (!ix->narrow && flc[best] > 2) flc[best] = (flc[best] + 1) / 2;
+    else if (tfc[best] > 1) tfc[best] = (tfc[best] + 1) / 2;
     else break;
   }
   std::vector<double> h;
@@ -382,16 +389,16 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   return PB_OK;
 }
 
-template <int F, int SC, bool G>
+template <int F, int SC, bool G, bool N>
 int launch_score_t(pb_batch* b, const ScoreParams& P, int grid, int threads, size_t smem) {
-  score_kernel<F, SC, G><<<grid, threads, smem, b->stream>>>(P);
+  score_kernel<F, SC, G, N><<<grid, threads, smem, b->stream>>>(P);
   CU(cudaGetLastError());
   return PB_OK;
 }
-template <int F, int SC, bool G>
+template <int F, int SC, bool G, bool N>
 int occupancy_score_t(int* per_sm, int threads, size_t smem) {
-  CU(cudaFuncSetAttribute(score_kernel<F, SC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G>, threads, smem));
+  CU(cudaFuncSetAttribute(score_kernel<F, SC, G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G, N>, threads, smem));
   return PB_OK;
 }
 
@@ -439,16 +446,21 @@ int launch_score(pb_batch* b, ScoreParams& P, bool gmode, uint64_t tiles) {
     P.tab_stride = 8u << sp.rep_shift;
     for (int x = 0; x < 4; ++x) P.tab_boff[x] = P.tab_off[x] * P.tab_stride;
     int per_sm = 1;
-    if (gmode) RC((occupancy_score_t<F, SC, true>(&per_sm, sp.threads, sp.smem)));
-    else RC((occupancy_score_t<F, SC, false>(&per_sm, sp.threads, sp.smem)));
+    const bool nw = b->ix->narrow;
+    if (gmode && nw) RC((occupancy_score_t<F, SC, true, true>(&per_sm, sp.threads, sp.smem)));
+    else if (gmode) RC((occupancy_score_t<F, SC, true, false>(&per_sm, sp.threads, sp.smem)));
+    else if (nw) RC((occupancy_score_t<F, SC, false, true>(&per_sm, sp.threads, sp.smem)));
+    else RC((occupancy_score_t<F, SC, false, false>(&per_sm, sp.threads, sp.smem)));
     if (per_sm < 1) { pb::set_error("scoring kernel does not fit an SM (%d threads, %zu B shared)", sp.threads, sp.smem); return PB_ERR_CUDA; }
     // one warp = one contiguous span of tiles; never more warps than there is work for
     const uint64_t warps_per_cta = (uint64_t)sp.threads / 32;
     uint64_t max_grid = (uint64_t)b->ix->sm_count * per_sm;
     uint64_t want = (tiles + warps_per_cta * 2 - 1) / (warps_per_cta * 2);
     int grid = (int)std::max<uint64_t>(1, std::min(max_grid, want));
-    if (gmode) return launch_score_t<F, SC, true>(b, P, grid, sp.threads, sp.smem);
-    return launch_score_t<F, SC, false>(b, P, grid, sp.threads, sp.smem);
+    if (gmode && nw) return launch_score_t<F, SC, true, true>(b, P, grid, sp.threads, sp.smem);
+    if (gmode) return launch_score_t<F, SC, true, false>(b, P, grid, sp.threads, sp.smem);
+    if (nw) return launch_score_t<F, SC, false, true>(b, P, grid, sp.threads, sp.smem);
+    return launch_score_t<F, SC, false, false>(b, P, grid, sp.threads, sp.smem);
   });
 }
 
@@ -923,7 +935,41 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
     CU(upload(ix->edge_child, im->edge_child, im->n_edges));
     CU(upload(ix->term_row_begin, im->term_row_begin, im->n_terms + 1));
     CU(upload(ix->term_byte_len, im->term_byte_len, im->n_terms));
-    CU(upload(ix->post_blocks, im->post_blocks, im->n_rows_padded * (1 + 2 * ix->F), (size_t)TILE_ROWS * (1 + 2 * ix->F)));
+    // Posting columns: when, per field, (tf, field length) packs into 16 bits, the device copy keeps one
+    // u16 code = tf << fl_bits | fl per field (4 + 2F bytes per row instead of 4 + 8F); the code is
+    // also the index into the field's BM25 table.  PB_POSTING_LAYOUT=wide|narrow|auto (default auto).
+    {
+      bool fits = true;
+      for (uint32_t f = 0; f < ix->F; ++f) {
+        ix->fl_bits[f] = bits_for((uint64_t)im->max_fl[f] + 1);
+        fits = fits && (((uint64_t)im->max_tf[f] + 1) << ix->fl_bits[f]) <= 65536ull;
+      }
+      uint64_t min_table = 0;       // the BM25 table keeps whole rows of 1 << fl_bits entries in the narrow layout
+      for (uint32_t f = 0; f < ix->F; ++f) min_table += 4ull << ix->fl_bits[f];
+      fits = fits && min_table <= 8192;
+      const char* e = std::getenv("PB_POSTING_LAYOUT");
+      if (e && !std::strcmp(e, "narrow") && !fits) { pb::set_error("PB_POSTING_LAYOUT=narrow but a (tf, field length) pair does not fit 16 bits"); return PB_ERR_UNSUPPORTED; }
+      ix->narrow = fits && !(e && !std::strcmp(e, "wide"));
+      const uint32_t NC = 1 + 2 * ix->F;
+      const uint64_t tiles = im->n_rows_padded / TILE_ROWS;
+      if (!ix->narrow) {
+        ix->tile_words = NC * TILE_ROWS;
+        CU(upload(ix->post_blocks, im->post_blocks, im->n_rows_padded * NC, (size_t)TILE_ROWS * NC));
+      } else {
+        ix->tile_words = TILE_ROWS + ix->F * (TILE_ROWS / 2);
+        std::vector<uint32_t> nb((size_t)(tiles + 1) * ix->tile_words, 0u);      // + one zero tile behind the spare tile
+        for (uint64_t t = 0; t < tiles; ++t) {
+          const uint32_t* src = im->post_blocks + t * (uint64_t)NC * TILE_ROWS;
+          uint32_t* dst = nb.data() + t * (uint64_t)ix->tile_words;
+          std::memcpy(dst, src, TILE_ROWS * sizeof(uint32_t));
+          uint16_t* codes = reinterpret_cast<uint16_t*>(dst + TILE_ROWS);
+          for (uint32_t f = 0; f < ix->F; ++f)
+            for (uint32_t r = 0; r < (uint32_t)TILE_ROWS; ++r)
+              codes[f * TILE_ROWS + r] = (uint16_t)((src[(1 + f) * TILE_ROWS + r] << ix->fl_bits[f]) | src[(1 + ix->F + f) * TILE_ROWS + r]);
+        }
+        CU(upload(ix->post_blocks, nb.data(), nb.size(), 0));
+      }
+    }
     ix->h_node_parent.assign(im->node_parent, im->node_parent + im->n_nodes);
     ix->h_node_char.assign(im->node_char, im->node_char + im->n_nodes);
     ix->h_term_node.assign(im->term_node, im->term_node + im->n_terms);

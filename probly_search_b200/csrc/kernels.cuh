@@ -66,7 +66,16 @@ struct IndexView {
   const uint32_t* edge_child;
   const uint64_t* term_row_begin;
   const uint32_t* term_byte_len;
-  const uint32_t* post_blocks;    // tile-blocked columns: [tile][1 + 2F][128] (pb_index_image)
+  // Posting columns in HBM, tile-blocked (one contiguous block per 128 rows):
+  //   wide   (any tf / field length):  [tile][doc u32 x128][tf0 u32 x128]..[fl(F-1) u32 x128]   = 4 + 8F bytes / row
+  //   narrow (chosen at pb_index_create when, per field, (max tf + 1) << fl_bits <= 65536 with
+  //          fl_bits = bits of the largest field length): one u16 code = tf << fl_bits | fl per field
+  //          [tile][doc u32 x128][code0 u16 x128]..[code(F-1) u16 x128]                          = 4 + 2F bytes / row
+  //          The code IS the index into the field's BM25 table (row stride 1 << fl_bits).
+  const uint32_t* post_blocks;
+  uint32_t tile_words;            // u32 words per tile: 128 (1 + 2F) wide, 128 + 64F narrow
+  uint32_t narrow;
+  uint32_t fl_bits[4];
   const uint32_t* removed;        // bitmap, bit set = doc not live
   const uint64_t* term_df_live;
   const uint32_t* term_live_rows; // rows of the term whose doc is live
@@ -80,15 +89,25 @@ struct IndexView {
   uint32_t has_removed;
 };
 
-// Random access into the tile-blocked columns (side path, live_df): column 0 = doc,
-// 1 + f = tf[f], 1 + F + f = fl[f].
-template <int F>
-__device__ __forceinline__ const uint32_t* row_ptr(const uint32_t* blocks, uint64_t row) {
-  return blocks + (row / TILE_ROWS) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + (row % TILE_ROWS);
+// Random access into the tile-blocked columns (side path, live_df, marking): column 0 = doc,
+// 1 + f = tf[f], 1 + F + f = fl[f].  Layout-aware at run time (these paths are not the hot loop).
+__device__ __forceinline__ const uint32_t* tile_ptr(const IndexView& ix, uint64_t tile) {
+  return ix.post_blocks + tile * (uint64_t)ix.tile_words;
 }
-template <int F> __device__ __forceinline__ uint32_t row_doc(const uint32_t* b, uint64_t r) { return row_ptr<F>(b, r)[0]; }
-template <int F> __device__ __forceinline__ uint32_t row_tf(const uint32_t* b, uint64_t r, int f) { return row_ptr<F>(b, r)[(1 + f) * TILE_ROWS]; }
-template <int F> __device__ __forceinline__ uint32_t row_fl(const uint32_t* b, uint64_t r, int f) { return row_ptr<F>(b, r)[(1 + F + f) * TILE_ROWS]; }
+__device__ __forceinline__ uint32_t row_doc(const IndexView& ix, uint64_t r) {
+  return tile_ptr(ix, r / TILE_ROWS)[r % TILE_ROWS];
+}
+__device__ __forceinline__ uint32_t row_col(const IndexView& ix, uint64_t r, int c) {   // c = 0 .. 2F-1 (tf.., fl..)
+  const uint32_t* t = tile_ptr(ix, r / TILE_ROWS) + TILE_ROWS;
+  if (ix.narrow) {
+    const uint32_t nf = ix.num_fields, f = (uint32_t)c < nf ? (uint32_t)c : (uint32_t)c - nf;
+    const uint32_t code = reinterpret_cast<const uint16_t*>(t)[f * TILE_ROWS + (r % TILE_ROWS)];
+    return (uint32_t)c < nf ? code >> ix.fl_bits[f] : code & ((1u << ix.fl_bits[f]) - 1u);
+  }
+  return t[c * TILE_ROWS + (r % TILE_ROWS)];
+}
+template <int F> __device__ __forceinline__ uint32_t row_tf(const IndexView& ix, uint64_t r, int f) { return row_col(ix, r, f); }
+template <int F> __device__ __forceinline__ uint32_t row_fl(const IndexView& ix, uint64_t r, int f) { return row_col(ix, r, F + f); }
 
 struct Outputs {
   unsigned long long* n_results;
@@ -175,16 +194,8 @@ struct ScoreParams {
 // ------------------------------------------------------------------------------------------
 // Posting tiles are streamed once per segment; how they travel is a tuning knob:
 //   PB_LDPOLICY 0: ld.global.nc.L1::no_allocate (pure stream)   1: ld.global.nc (allocates in L1)
-//   PB_PF 0: no prefetch   1: prefetch.global.L1 of a later tile, one 128 B line per lane (20 lanes at F = 2)
-//   PB_PF_DIST: how many tiles ahead
 #ifndef PB_LDPOLICY
 #define PB_LDPOLICY 0
-#endif
-#ifndef PB_PF
-#define PB_PF 0
-#endif
-#ifndef PB_PF_DIST
-#define PB_PF_DIST 1
 #endif
 __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
   uint4 r;
@@ -199,8 +210,6 @@ __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
 #endif
   return r;
 }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -444,13 +453,12 @@ __global__ void live_df_kernel(IndexView ix, unsigned long long* __restrict__ df
     uint64_t a = ix.term_row_begin[t], b = ix.term_row_begin[t + 1];
     unsigned long long s = 0, n = 0;
     for (uint64_t r = a + lane; r < b; r += 32) {
-      const uint32_t* rp = row_ptr<F>(ix.post_blocks, r);
-      uint32_t d = rp[0];
+      uint32_t d = row_doc(ix, r);
       bool live = !((ix.removed[d >> 5] >> (d & 31)) & 1u);
       if (live) {
         ++n;
 #pragma unroll
-        for (int f = 0; f < F; ++f) s += rp[(1 + f) * TILE_ROWS];
+        for (int f = 0; f < F; ++f) s += row_col(ix, r, f);
       }
     }
     s = warp_sum_u64(s);
@@ -694,7 +702,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
       if (exact) xtiles += tend - t;
       for (; t < tend; ++t) {
         uint64_t row0 = (abs0 + (t - st0)) * TILE_ROWS + lane * 4;
-        uint4 d = ldg_stream(P.ix.post_blocks + (abs0 + (t - st0)) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 4);
+        uint4 d = ldg_stream(tile_ptr(P.ix, abs0 + (t - st0)) + lane * 4);
         uint32_t dv[4] = {d.x, d.y, d.z, d.w};
         bool inr[4];
 #pragma unroll
@@ -725,7 +733,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
             for (int j = 0; j < 4; ++j) {
               if (lo[j] < hi[j]) {
                 const uint64_t mid = (lo[j] + hi[j]) >> 1;
-                if (row_doc<F>(P.ix.post_blocks, mid) < dv[j]) lo[j] = mid + 1; else hi[j] = mid;
+                if (row_doc(P.ix, mid) < dv[j]) lo[j] = mid + 1; else hi[j] = mid;
                 more = true;
               }
             }
@@ -736,7 +744,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
             if (!inr[j]) continue;
             uint32_t inc = 1u;
             const uint64_t r = lo[j];
-            if (r < pend && row_doc<F>(P.ix.post_blocks, r) == dv[j]) {
+            if (r < pend && row_doc(P.ix, r) == dv[j]) {
               const uint32_t bit = 1u << (r & 31);
               const uint32_t old = atomicOr(&sm[(r / TILE_ROWS - pabs0) * 4 + ((r % TILE_ROWS) >> 5)], bit);
               inc = (old & bit) ? 1u : 2u;
@@ -761,6 +769,29 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
 // 128-bit streaming load (fully coalesced 512 B per column per warp).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t u4c(const uint4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+// A lane's 4 rows of a tile.  Wide layout: a uint4 per tf / field-length column.  Narrow layout: a
+// uint2 per field holding four u16 codes (tf << fl_bits | fl).
+template <int F, bool NARROW> struct TileRegs;
+template <int F> struct TileRegs<F, false> {
+  uint4 dq;
+  uint4 tq[F], lq[F];
+  uint32_t mw;      // GMODE primary list: the row-mask word holding this lane's 4 bits
+  __device__ __forceinline__ uint32_t tf(const IndexView&, int f, int j) const { return u4c(tq[f], j); }
+  __device__ __forceinline__ uint32_t fl(const IndexView&, int f, int j) const { return u4c(lq[f], j); }
+  // index into field f's table of saturated tf (row stride flcap)
+  __device__ __forceinline__ uint32_t tabidx(int f, int j, uint32_t flcap) const { return u4c(tq[f], j) * flcap + u4c(lq[f], j); }
+};
+template <int F> struct TileRegs<F, true> {
+  uint4 dq;
+  uint2 cq[F];
+  uint32_t mw;
+  __device__ __forceinline__ uint32_t code(int f, int j) const {       // one PRMT
+    return __byte_perm(j < 2 ? cq[f].x : cq[f].y, 0u, (j & 1) ? 0x4432u : 0x4410u);
+  }
+  __device__ __forceinline__ uint32_t tf(const IndexView& ix, int f, int j) const { return code(f, j) >> ix.fl_bits[f]; }
+  __device__ __forceinline__ uint32_t fl(const IndexView& ix, int f, int j) const { return code(f, j) & ((1u << ix.fl_bits[f]) - 1u); }
+  __device__ __forceinline__ uint32_t tabidx(int f, int j, uint32_t) const { return code(f, j); }   // flcap == 1 << fl_bits
+};
 
 // BM25::score (bm25.rs:60-93) for the 4 rows of a lane:  score += ((tf' * idf) * boost[x]) * eb.
 // TABFULL: every (tf, fl) of the index is inside the shared-memory table of tf' (no range check,
@@ -771,19 +802,22 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
-template <int F, bool TABFULL, int SIMPLE>
-__device__ __forceinline__ void bm25_rows(const ScoreParams& P, const uint32_t tbase, const uint4 (&tq)[F],
-                                          const uint4 (&lq)[F], double idf, double ebst, double (&sc)[4]) {
+template <int F, bool TABFULL, int SIMPLE, bool NARROW>
+__device__ __forceinline__ void bm25_rows(const ScoreParams& P, const uint32_t tbase, const TileRegs<F, NARROW>& R,
+                                          double idf, double ebst, double (&sc)[4]) {
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     const uint32_t fbase = tbase + P.tab_boff[f];     // this lane's copy of field f's table (shared address)
     const uint32_t flcap = P.tab_flcap[f];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t tf = u4c(tq[f], j), fl = u4c(lq[f], j);
       double tfn;
-      if (TABFULL) tfn = lds_f64(fbase + (tf * flcap + fl) * P.tab_stride);
-      else tfn = (tf < P.tab_tfcap[f] && fl < flcap) ? lds_f64(fbase + (tf * flcap + fl) * P.tab_stride) : bm25_tf_slow(P, tf, fl, f);
+      if (TABFULL) {
+        tfn = lds_f64(fbase + R.tabidx(f, j, flcap) * P.tab_stride);
+      } else {
+        const uint32_t tf = R.tf(P.ix, f, j), fl = R.fl(P.ix, f, j);
+        tfn = (tf < P.tab_tfcap[f] && fl < flcap) ? lds_f64(fbase + (tf * flcap + fl) * P.tab_stride) : bm25_tf_slow(P, tf, fl, f);
+      }
       double c = __dmul_rn(tfn, idf);
       if (SIMPLE == 0) c = __dmul_rn(c, P.boost[f]);     // x * 1.0 == x exactly, so levels 1 / 2 may skip
       if (SIMPLE < 2) c = __dmul_rn(c, ebst);
@@ -792,8 +826,9 @@ __device__ __forceinline__ void bm25_rows(const ScoreParams& P, const uint32_t t
         // adding it is an exact identity: no select needed (the reference skips tf = 0, bm25.rs:73)
         if (f == 0) sc[j] = c; else sc[j] = __dadd_rn(sc[j], c);
       } else {
-        if (f == 0) sc[j] = tf > 0 ? c : 0.0;
-        else if (tf > 0) sc[j] = __dadd_rn(sc[j], c);
+        const bool hit = R.tf(P.ix, f, j) > 0;
+        if (f == 0) sc[j] = hit ? c : 0.0;
+        else if (hit) sc[j] = __dadd_rn(sc[j], c);
       }
     }
   }
@@ -801,8 +836,8 @@ __device__ __forceinline__ void bm25_rows(const ScoreParams& P, const uint32_t t
 
 // Single-event ZeroToOne (score() + finalize(), zero_to_one.rs:44-126): max over fields of
 // min(s/tf, 1) * tf / max(field_length, query_terms_len), floored at 0.
-template <int F>
-__device__ __forceinline__ void z2o_rows(const uint4 (&tq)[F], const uint4 (&lq)[F], double zs, uint32_t qtl,
+template <int F, bool NARROW>
+__device__ __forceinline__ void z2o_rows(const ScoreParams& P, const TileRegs<F, NARROW>& R, double zs, uint32_t qtl,
                                          double (&sc)[4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) sc[j] = 0.0;
@@ -810,7 +845,7 @@ __device__ __forceinline__ void z2o_rows(const uint4 (&tq)[F], const uint4 (&lq)
   for (int f = 0; f < F; ++f) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t tf = u4c(tq[f], j), fl = u4c(lq[f], j);
+      const uint32_t tf = R.tf(P.ix, f, j), fl = R.fl(P.ix, f, j);
       if (tf > 0) sc[j] = fmax(z2o_entry(zs, tf, fl, qtl), sc[j]);
     }
   }
@@ -859,42 +894,53 @@ struct SegCtx {
   uint32_t shift;           // GMODE: log2(bin width in docs)
 };
 
-// One tile = 128 aligned rows; lane l owns rows 4l..4l+3 (one 128-bit load per column).
+// One tile = 128 aligned rows; lane l owns rows 4l..4l+3 (one 128-bit load per u32 column, one
+// 32-bit load per u8 column).
 //   EDGE : the tile is shared with neighbouring segments -> per-row range mask
 //   FAST : no removed docs, no full-result capture, complete BM25 table -> no per-row checks
-template <int F>
-struct TileRegs {
-  uint4 dq;
-  uint4 tq[F], lq[F];
-  uint32_t mw;      // GMODE primary list: the row-mask word holding this lane's 4 bits
+template <int F, bool NARROW> struct TileGeom {
+  static constexpr uint32_t WORDS = NARROW ? (TILE_ROWS + F * TILE_ROWS / 2) : (1 + 2 * F) * TILE_ROWS;   // u32 words per tile
 };
-template <int F, bool GMODE>
-__device__ __forceinline__ void load_tile(const ScoreParams& P, const SegCtx& C, uint64_t tile_row, int lane, TileRegs<F>& R) {
-  // one contiguous (1 + 2F) x 512 B block per tile: a single base address, immediate column offsets
-  const uint32_t* base = P.ix.post_blocks + (tile_row / TILE_ROWS) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 4;
-  R.mw = 0;
-  if (GMODE && C.mode == MODE_PRIMARY) {
-    // address known before any posting data arrives: travels together with the tile
-    uint32_t* wp = C.rowmask + (tile_row / TILE_ROWS - C.rbeg / TILE_ROWS) * 4 + (lane >> 3);
-    asm volatile("ld.global.u32 %0, [%1];" : "=r"(R.mw) : "l"(wp));
-    if (R.mw != 0u && (lane & 7) == 0) *wp = 0u;      // consumed: the pool is clean again for the next round
-  }
-  R.dq = ldg_stream(base);
+__device__ __forceinline__ uint2 ldg_stream_u64(const uint32_t* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t* rowmask_word(const SegCtx& C, uint64_t tile_row, int lane) {
+  return C.rowmask + (tile_row / TILE_ROWS - C.rbeg / TILE_ROWS) * 4 + (lane >> 3);
+}
+template <int F>
+__device__ __forceinline__ void load_cols(TileRegs<F, false>& R, const uint32_t* base, int lane) {
 #pragma unroll
   for (int f = 0; f < F; ++f) {
-    R.tq[f] = ldg_stream(base + (1 + f) * TILE_ROWS);
-    R.lq[f] = ldg_stream(base + (1 + F + f) * TILE_ROWS);
+    R.tq[f] = ldg_stream(base + (1 + f) * TILE_ROWS + lane * 4);
+    R.lq[f] = ldg_stream(base + (1 + F + f) * TILE_ROWS + lane * 4);
   }
 }
+template <int F>
+__device__ __forceinline__ void load_cols(TileRegs<F, true>& R, const uint32_t* base, int lane) {
+  // u16 code columns: 256 bytes each behind the doc column; this lane's 4 rows are one 8-byte load
+#pragma unroll
+  for (int f = 0; f < F; ++f) R.cq[f] = ldg_stream_u64(base + TILE_ROWS + f * (TILE_ROWS / 2) + lane * 2);
+}
+template <int F, bool GMODE, bool NARROW>
+__device__ __forceinline__ void load_tile(const ScoreParams& P, const SegCtx& C, uint64_t tile_row, int lane, TileRegs<F, NARROW>& R) {
+  // one contiguous block per tile: a single base address, immediate column offsets
+  const uint32_t* base = P.ix.post_blocks + (tile_row / TILE_ROWS) * (uint64_t)TileGeom<F, NARROW>::WORDS;
+  R.mw = 0;
+  if (GMODE && C.mode == MODE_PRIMARY) {
+    // the address does not depend on posting data: the mask word travels together with the tile
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(R.mw) : "l"(rowmask_word(C, tile_row, lane)));
+  }
+  R.dq = ldg_stream(base + lane * 4);
+  load_cols(R, base, lane);
+}
 
-template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE>
+template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE, bool NARROW>
 __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
-                                             const TileRegs<F>& R, uint64_t tile_row, int lane, WarpAcc& acc,
+                                             const TileRegs<F, NARROW>& R, uint64_t tile_row, int lane, WarpAcc& acc,
                                              uint32_t& st_div) {
-  const uint64_t row0 = tile_row + lane * 4;
   const uint4 dq = R.dq;
-  const uint4 (&tq)[F] = R.tq;
-  const uint4 (&lq)[F] = R.lq;
   const uint32_t dv[4] = {dq.x, dq.y, dq.z, dq.w};
   uint32_t valid = 0xFu;
   if (EDGE) {
@@ -915,9 +961,9 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
   double sc[4];
   uint32_t some = valid;
   if (SCORER == 0) {
-    if (FAST) bm25_rows<F, true, SIMPLE>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
-    else if (P.tab_full) bm25_rows<F, true, 0>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
-    else bm25_rows<F, false, 0>(P, s_tab, tq, lq, C.idf, C.ebst, sc);
+    if (FAST) bm25_rows<F, true, SIMPLE, NARROW>(P, s_tab, R, C.idf, C.ebst, sc);
+    else if (P.tab_full) bm25_rows<F, true, 0, NARROW>(P, s_tab, R, C.idf, C.ebst, sc);
+    else bm25_rows<F, false, 0, NARROW>(P, s_tab, R, C.idf, C.ebst, sc);
     // Some(score) only if score > 0 (bm25.rs:89-92).  A double whose high word, read as a signed
     // integer, lies in (0, 0x7FF00000) is a positive finite number: when that holds for the four
     // rows of the lane (two integer min/max) the per-row f64 compares are skipped.
@@ -932,7 +978,7 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
         if (!(sc[j] > 0.0)) some &= ~(1u << j);
     }
   } else {
-    z2o_rows<F>(tq, lq, C.zs, C.qtl, sc);
+    z2o_rows<F, NARROW>(P, R, C.zs, C.qtl, sc);
   }
   if (GMODE) {
     // rows that must take the ordered per-doc fold instead: every live row of a secondary list
@@ -941,6 +987,8 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
     uint32_t dmask = valid;
     if (C.mode == MODE_PRIMARY) {
       dmask = (R.mw >> ((lane & 7) * 4)) & valid;
+      // consumed: the pool is clean again for the next round (only the warp that scores the tile clears it)
+      if (R.mw != 0u && (lane & 7) == 0) *rowmask_word(C, tile_row, lane) = 0u;
     } else if (C.mode != MODE_SECONDARY) {
       dmask = 0;
       bool maybe = true;
@@ -973,7 +1021,7 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
           } else {
             uint32_t tfj[F], flj[F];
 #pragma unroll
-            for (int f = 0; f < F; ++f) { tfj[f] = u4c(tq[f], j); flj[f] = u4c(lq[f], j); }
+            for (int f = 0; f < F; ++f) { tfj[f] = R.tf(P.ix, f, j); flj[f] = R.fl(P.ix, f, j); }
             pay = z2o_pack<F>(tfj, flj);
           }
           if (pos < P.bin_off[bin + 1]) P.rec[pos] = make_uint4(dv[j], C.seg, (uint32_t)pay, (uint32_t)(pay >> 32));
@@ -987,33 +1035,35 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
   else acc.template add4<true>(P.out, some, dv, sc, lane);
 }
 
-template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE>
+template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE, bool NARROW>
 __device__ __forceinline__ void process_tile(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                              uint64_t tile_row, int lane, WarpAcc& acc, uint32_t& st_div) {
-  TileRegs<F> R;
-  load_tile<F, GMODE>(P, C, tile_row, lane, R);
-  compute_tile<F, SCORER, GMODE, EDGE, FAST, SIMPLE>(P, s_tab, C, R, tile_row, lane, acc, st_div);
+  TileRegs<F, NARROW> R;
+  load_tile<F, GMODE, NARROW>(P, C, tile_row, lane, R);
+  compute_tile<F, SCORER, GMODE, EDGE, FAST, SIMPLE, NARROW>(P, s_tab, C, R, tile_row, lane, acc, st_div);
 }
 
-// Interior tiles of one segment (every row belongs to the segment).
-template <int F, int SCORER, bool GMODE, bool FAST, int SIMPLE>
+// Interior tiles of one segment (every row belongs to the segment).  In the narrow layout a tile is
+// only 5 + 2F registers per lane, so the loop is software-pipelined: the loads of tile i + 1 are in
+// flight while tile i is scored (the spare tile behind the last row and the pad words of the row
+// masks make the look-ahead load safe; nothing read ahead is used or cleared unless it is scored).
+template <int F, int SCORER, bool GMODE, bool FAST, int SIMPLE, bool NARROW>
 __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                                uint64_t tile_row, uint32_t n_tiles, int lane, WarpAcc& acc,
                                                uint32_t& st_div) {
-  for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS) {
-#if PB_PF
-    // pull a later tile of this list towards the SM while this one is scored: a tile is one contiguous
-    // block of (1 + 2F) x 512 B = 4 (1 + 2F) lines, one line per lane
-    if (i + PB_PF_DIST < n_tiles && lane < 4 * (1 + 2 * F)) {
-      const uint32_t* nb = P.ix.post_blocks + (tile_row / TILE_ROWS + PB_PF_DIST) * (uint64_t)((1 + 2 * F) * TILE_ROWS) + lane * 32;
-#if PB_PF == 1
-      prefetch_l1(nb);
-#else
-      prefetch_l2(nb);
-#endif
+  if (NARROW) {
+    if (n_tiles == 0) return;
+    TileRegs<F, NARROW> cur;
+    load_tile<F, GMODE, NARROW>(P, C, tile_row, lane, cur);
+    for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS) {
+      TileRegs<F, NARROW> nxt;
+      load_tile<F, GMODE, NARROW>(P, C, tile_row + TILE_ROWS, lane, nxt);
+      compute_tile<F, SCORER, GMODE, false, FAST, SIMPLE, NARROW>(P, s_tab, C, cur, tile_row, lane, acc, st_div);
+      cur = nxt;
     }
-#endif
-    process_tile<F, SCORER, GMODE, false, FAST, SIMPLE>(P, s_tab, C, tile_row, lane, acc, st_div);
+  } else {
+    for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS)
+      process_tile<F, SCORER, GMODE, false, FAST, SIMPLE, NARROW>(P, s_tab, C, tile_row, lane, acc, st_div);
   }
 }
 
@@ -1022,7 +1072,7 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
 // whatever the shared-memory table costs: 3 x 256, 2 x 384 or 1 x 768 threads.
 constexpr int SCORE_MAX_THREADS = 768;
 
-template <int F, int SCORER, bool GMODE>
+template <int F, int SCORER, bool GMODE, bool NARROW>
 __global__ void __launch_bounds__(SCORE_MAX_THREADS, 1) score_kernel(const __grid_constant__ ScoreParams P) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   if (SCORER == 0) {
@@ -1091,21 +1141,21 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 1) score_kernel(const __gri
       const uint64_t int1 = st1 - ((C.rend % TILE_ROWS) ? 1 : 0);     // may be < int0 for a tiny segment
       const uint64_t ia = min(max(t, int0), tend), ib = max(min(tend, int1), ia);
       for (; t < ia; ++t)
-        process_tile<F, SCORER, GMODE, true, false, 0>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
+        process_tile<F, SCORER, GMODE, true, false, 0, NARROW>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
       {
         const uint64_t row = (abs0 + (t - st0)) * TILE_ROWS;
         const uint32_t n = (uint32_t)(ib - t);
         if (fast) {
-          if (simple) interior_tiles<F, SCORER, GMODE, true, 2>(P, s_tab, C, row, n, lane, acc, st_div);
-          else if (P.boosts_all_one) interior_tiles<F, SCORER, GMODE, true, 1>(P, s_tab, C, row, n, lane, acc, st_div);
-          else interior_tiles<F, SCORER, GMODE, true, 0>(P, s_tab, C, row, n, lane, acc, st_div);
+          if (simple) interior_tiles<F, SCORER, GMODE, true, 2, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
+          else if (P.boosts_all_one) interior_tiles<F, SCORER, GMODE, true, 1, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
+          else interior_tiles<F, SCORER, GMODE, true, 0, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
         } else {
-          interior_tiles<F, SCORER, GMODE, false, 0>(P, s_tab, C, row, n, lane, acc, st_div);
+          interior_tiles<F, SCORER, GMODE, false, 0, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
         }
         t = ib;
       }
       for (; t < tend; ++t)
-        process_tile<F, SCORER, GMODE, true, false, 0>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
+        process_tile<F, SCORER, GMODE, true, false, 0, NARROW>(P, s_tab, C, (abs0 + (t - st0)) * TILE_ROWS, lane, acc, st_div);
     }
     ++s;
   }
@@ -1137,7 +1187,7 @@ __device__ __forceinline__ double bm25_row_score(const ScoreParams& P, const Seg
   double score = 0.0;
 #pragma unroll
   for (int f = 0; f < F; ++f) {
-    uint32_t tf = row_tf<F>(P.ix.post_blocks, row, f), fl = row_fl<F>(P.ix.post_blocks, row, f);
+    uint32_t tf = row_tf<F>(P.ix, row, f), fl = row_fl<F>(P.ix, row, f);
     if (tf > 0) {
       double tfn = (tf < P.tab_tfcap[f] && fl < P.tab_flcap[f]) ? P.tab[P.tab_off[f] + tf * P.tab_flcap[f] + fl]
                                                                  : bm25_tf_slow(P, tf, fl, f);
@@ -1197,12 +1247,12 @@ __device__ __noinline__ bool fold_group_slow(const FoldParams& FP, uint32_t i, u
           if ((done_lo >> j) & 1ull) continue;
           unsigned long long v = FP.val[i + j];
           uint32_t row = (uint32_t)v;
-          uint32_t tf = row_tf<F>(P.ix.post_blocks, row, x);
+          uint32_t tf = row_tf<F>(P.ix, row, x);
           if (tf == 0) { done_lo |= 1ull << j; continue; }
           const Seg sg = P.segs[(uint32_t)(v >> 32)];
           double sc = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
           if (bj < 0 || sc > bs || (sc == bs && v < bv)) {
-            bj = (int)j; bs = sc; bv = v; btf = tf; bfl = row_fl<F>(P.ix.post_blocks, row, x); bterm = sg.term; bqti = sg.qti;
+            bj = (int)j; bs = sc; bv = v; btf = tf; bfl = row_fl<F>(P.ix, row, x); bterm = sg.term; bqti = sg.qti;
           }
         }
         if (bj < 0) break;
@@ -1422,7 +1472,7 @@ __global__ void __launch_bounds__(CTA_THREADS) fold_kernel(const __grid_constant
       } else {
         ev_score = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
 #pragma unroll
-        for (int f = 0; f < F; ++f) { tfv[f] = row_tf<F>(P.ix.post_blocks, row, f); flv[f] = row_fl<F>(P.ix.post_blocks, row, f); }
+        for (int f = 0; f < F; ++f) { tfv[f] = row_tf<F>(P.ix, row, f); flv[f] = row_fl<F>(P.ix, row, f); }
       }
     }
     fold_window<F, SCORER, false>(P, acc, lane, in, head, hm, advance, q, doc, val, ev_score, (uint32_t)sg.qti, sg.term, tfv, flv);
@@ -1437,7 +1487,7 @@ __device__ __forceinline__ uint32_t find_row(const ScoreParams& P, const Seg& sg
   uint64_t lo = sg.row_begin, hi = sg.row_begin + sg.n_rows;
   while (lo < hi) {
     uint64_t mid = (lo + hi) >> 1;
-    if (row_doc<F>(P.ix.post_blocks, mid) < doc) lo = mid + 1; else hi = mid;
+    if (row_doc(P.ix, mid) < doc) lo = mid + 1; else hi = mid;
   }
   return (uint32_t)lo;
 }
@@ -1559,7 +1609,7 @@ __global__ void __launch_bounds__(CTA_THREADS) binfold_kernel(const __grid_const
           const Seg sg2 = P.segs[s_seg];
           const uint32_t row = find_row<F>(P, sg2, doc);
 #pragma unroll
-          for (int f = 0; f < F; ++f) { tfv[f] = row_tf<F>(P.ix.post_blocks, row, f); flv[f] = row_fl<F>(P.ix.post_blocks, row, f); }
+          for (int f = 0; f < F; ++f) { tfv[f] = row_tf<F>(P.ix, row, f); flv[f] = row_fl<F>(P.ix, row, f); }
         } else {
           z2o_unpack<F>(pay, tfv, flv);
         }
