@@ -325,16 +325,29 @@ def main():
     # ---- roofline of the dominant kernel (the single launch over all single-list queries)
     F = cfg.n_fields
     peak, peak_src = hbm_peak()
-    algo_bytes = st["rows_streamed_direct"] * (4 + 8 * F)
+    lay = ix.device_layout()
+    bpr = lay["bytes_per_row"]                      # 4 + 2F (u16 codes) or 4 + 8F (u32 columns): DESIGN.md section 3
+    algo_bytes = st["rows_streamed_direct"] * bpr
     launch_ms = st["ms_score"] / max(st["score_launches"], 1)
     achieved = algo_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "pbk::score_kernel<F=2,BM25,direct>", "achieved": achieved, "peak": peak,
+    # the two measured ceilings of a streaming read on THIS box: L2 -> SM fabric and HBM
+    ceilings = {}
+    if rank == 0:
+        for name, nbytes, iters in (("l2_read_gbs", 64 << 20, 50), ("hbm_read_gbs", 4 << 30, 5)):
+            g = C.c_double(0.0)
+            if L.pb_device_read_bandwidth(local_rank, nbytes, iters, C.byref(g)) == 0:
+                ceilings[name] = g.value
+    roofline = {"bound": "hbm", "kernel": f"pbk::score_kernel<F={F},{cfg.scorer},direct,{'narrow' if lay['narrow'] else 'wide'}>",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "bytes_per_row": bpr, "posting_layout": "u16 (tf,fl) codes" if lay["narrow"] else "u32 columns",
                 "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_ms,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                 "traffic_source": (traffic or {}).get("source"),
-                "share_of_step": st["ms_score"] / st["ms_total"] if st["ms_total"] else None}
+                "share_of_step": st["ms_score"] / st["ms_total"] if st["ms_total"] else None,
+                "measured_stream_ceilings": ceilings,
+                "rows_per_sec_this_launch": st["rows_streamed_direct"] / (launch_ms * 1e-3) if launch_ms > 0 else None}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on the host cores, bounded sample
     cpu = None

@@ -154,6 +154,25 @@ int pb_index_expand_term(pb_index* ix, const uint8_t* term, uint64_t term_len, u
 /* Per-term live occurrence count as the device computed it (tests). */
 int pb_index_term_df_live(pb_index* ix, uint64_t* out, uint64_t cap);
 
+/* How the posting columns are held in HBM.  The image above always carries u32 columns; at
+ * pb_index_create the device copy becomes NARROW when, for every field,
+ * (max tf + 1) << bits(max field length) <= 65536: one u16 code = tf << fl_bits | fl per field,
+ * i.e. 4 + 2F bytes per row instead of 4 + 8F.  Results do not depend on the layout.
+ * (Environment override for tests: PB_POSTING_LAYOUT=wide|narrow|auto.) */
+typedef struct pb_device_layout {
+  uint32_t narrow;              /* 1: u16 (tf, fl) codes, 0: u32 tf and field-length columns */
+  uint32_t bytes_per_row;       /* 4 + 2F or 4 + 8F: the bytes the scoring kernel reads per posting row */
+  uint32_t fl_bits[PB_MAX_FIELDS];
+  uint64_t posting_bytes;       /* HBM held by the posting columns */
+} pb_device_layout;
+int pb_index_device_layout(pb_index* ix, pb_device_layout* out);
+
+/* Diagnostic used by bench.py: read bandwidth (GB/s) of a plain streaming kernel (128-bit loads,
+ * grid = 8 CTAs per SM) over a private buffer of `bytes`, averaged over `iters` passes after one
+ * warm-up pass.  A buffer well below the 126 MB L2 measures the L2 -> SM fabric, a multi-GB buffer
+ * measures HBM: the two ceilings the scoring kernel is compared with. */
+int pb_device_read_bandwidth(int device, uint64_t bytes, uint32_t iters, double* gb_per_s);
+
 /* ------------------------------------------------------------------------------------------
  * Queries (replaces Index::query, src/query.rs:21-106, for batches)
  * ---------------------------------------------------------------------------------------- */

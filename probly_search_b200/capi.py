@@ -54,6 +54,11 @@ class IndexImage(C.Structure):
                 ("n_live_docs", C.c_uint64), ("field_avg", C.c_double * PB_MAX_FIELDS)]
 
 
+class DeviceLayout(C.Structure):
+    _fields_ = [("narrow", C.c_uint32), ("bytes_per_row", C.c_uint32), ("fl_bits", C.c_uint32 * PB_MAX_FIELDS),
+                ("posting_bytes", C.c_uint64)]
+
+
 class QueryBatchDesc(C.Structure):
     _fields_ = [("n_queries", C.c_uint64), ("query_term_off", C.c_void_p), ("term_byte_off", C.c_void_p),
                 ("term_bytes", C.c_void_p), ("scorer", C.c_uint32), ("bm25_k1", C.c_double),
@@ -84,7 +89,7 @@ EXPORTS = [
     "pb_builder_create", "pb_builder_destroy", "pb_builder_add_document", "pb_builder_add_documents",
     "pb_builder_remove_document", "pb_builder_vacuum", "pb_builder_get_info", "pb_builder_flatten",
     "pb_device_count", "pb_index_create", "pb_index_set_live_state", "pb_index_destroy",
-    "pb_index_expand_term", "pb_index_term_df_live", "pb_query_batch", "pb_batch_create", "pb_batch_run",
+    "pb_index_expand_term", "pb_index_term_df_live", "pb_index_device_layout", "pb_device_read_bandwidth", "pb_query_batch", "pb_batch_create", "pb_batch_run",
     "pb_batch_fetch", "pb_batch_destroy", "pb_batch_device_results", "pb_batch_get_stats", "pb_index_last_stats", "pb_query_full",
     "pb_host_alloc", "pb_host_free", "pb_last_error", "pb_version",
 ]
@@ -126,6 +131,8 @@ def lib() -> C.CDLL:
         "pb_index_destroy": (None, [vp]),
         "pb_index_expand_term": (i32, [vp, vp, u64, vp, u64, P(u64), P(u64)]),
         "pb_index_term_df_live": (i32, [vp, vp, u64]),
+        "pb_index_device_layout": (i32, [vp, vp]),
+        "pb_device_read_bandwidth": (i32, [i32, u64, C.c_uint32, vp]),
         "pb_query_batch": (i32, [vp, P(QueryBatchDesc), P(QueryResults)]),
         "pb_batch_create": (i32, [vp, P(QueryBatchDesc), P(vp)]),
         "pb_batch_run": (i32, [vp]),

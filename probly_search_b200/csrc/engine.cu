@@ -212,7 +212,7 @@ struct pb_batch {
   DBuf<ull> xcount;
   DBuf<uint32_t> bin_count, bin_off, bin_cursor;
   DBuf<uint4> rec;
-  DBuf<ull> s_tiles, s_tile_off, g_tiles, g_tile_off;
+  DBuf<ull> s_tiles, s_tile_off, g_tiles, g_tile_off, g_mtiles, g_mtile_off;
   DBuf<Seg> seg_s, seg_g;
   DBuf<uint8_t> cub_temp;
   // outputs
@@ -571,6 +571,7 @@ int batch_run(pb_batch* b) {
     CU(b->seg_g.ensure(n_gsegs + 1));
     CU(b->g_tiles.ensure(n_gsegs + 2));
     CU(b->g_tile_off.ensure(n_gsegs + 2));
+    CU(b->g_mtiles.ensure(n_gsegs + 2)); CU(b->g_mtile_off.ensure(n_gsegs + 2));
     gfill_kernel<<<ix->sm_count * 8, 256, 0, st>>>(view, NT, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p, b->qt_len.p,
                                                    b->qt_q.p, b->qt_gcount.p, b->qt_goff.p, b->seg_g.p, b->g_tiles.p,
                                                    b->q_prim.p, b->stats.p + ST_COUNT);
@@ -707,11 +708,16 @@ int batch_run(pb_batch* b) {
       P.bin_count = b->bin_count.p; P.bin_off = b->bin_off.p; P.bin_cursor = b->bin_cursor.p;
       CU(cudaMemsetAsync(b->bin_count.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
       CU(cudaMemsetAsync(b->bin_cursor.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
-      gslot_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, b->q_scheme.p, (uint32_t)r.qa);
+      gslot_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(b->seg_g.p, r.sa, r.sb, b->q_gidx.p, b->q_scheme.p, (uint32_t)r.qa,
+                                                                       b->g_tiles.p, b->g_mtiles.p);
       CU(cudaGetLastError());
-      int mgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->sm_count * 8, (tiles + 15) / 16));
+      RC(scan_ull(b, b->g_mtiles.p + r.sa, b->g_mtile_off.p + r.sa, nseg + 1));
+      launches += 2;
+      ScoreParams PM = P;                      // the marking pass walks its own tile space
+      PM.tile_off = (const uint64_t*)b->g_mtile_off.p;
+      int mgrid = ix->sm_count * 8;            // the size of the marking tile space is only known on the device
       CU(cudaMemsetAsync(b->xcount.p, 0, 2 * sizeof(ull), st));
-      RC(launch_mark(b, P, mgrid, 0));
+      RC(launch_mark(b, PM, mgrid, 0));
       launches += 2;
       ull h_x[2] = {0, 0};
       CU(cudaMemcpyAsync(h_x, b->xcount.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -726,7 +732,7 @@ int batch_run(pb_batch* b) {
         if (!scored || exact_tiles * TILE_ROWS * 4 > r.words * 4) {
           CU(cudaMemsetAsync(b->bitmap.p, 0, (size_t)(r.words + 4) * sizeof(uint32_t), st));
         } else {
-          RC(launch_mark(b, P, mgrid, 1));
+          RC(launch_mark(b, PM, mgrid, 1));
           ++launches;
         }
         return PB_OK;
@@ -1012,6 +1018,62 @@ int pb_index_term_df_live(pb_index* ix, uint64_t* out, uint64_t cap) {
   if (!ix || !out) return PB_ERR_INVALID;
   if (cap < ix->n_terms) { pb::set_error("pb_index_term_df_live: need %llu entries", (ull)ix->n_terms); return PB_ERR_CAPACITY; }
   for (uint64_t t = 0; t < ix->n_terms; ++t) out[t] = ix->h_df_live[t];
+  return PB_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) read_bw_kernel(const uint4* __restrict__ p, uint64_t n, uint32_t passes, unsigned long long* sink) {
+  const uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t acc = 0;
+  for (uint32_t pass = 0; pass < passes; ++pass) {     // several passes per launch: launch gaps do not count
+    uint64_t i = i0;
+    for (; i + 3 * stride < n; i += 4 * stride) {      // four independent 128-bit loads in flight per thread
+      uint4 a = ldg_stream((const uint32_t*)(p + i)), b = ldg_stream((const uint32_t*)(p + i + stride));
+      uint4 c = ldg_stream((const uint32_t*)(p + i + 2 * stride)), d = ldg_stream((const uint32_t*)(p + i + 3 * stride));
+      acc += (a.x ^ b.y) + (c.z ^ d.w);
+    }
+    for (; i < n; i += stride) acc += ldg_stream((const uint32_t*)(p + i)).x;
+  }
+  if (acc == 0x9E3779B9u) atomicAdd(sink, 1ull);      // keeps the loads alive
+}
+}  // namespace
+
+int pb_device_read_bandwidth(int device, uint64_t bytes, uint32_t iters, double* gb_per_s) {
+  if (!gb_per_s || bytes < 4096 || iters == 0) { pb::set_error("pb_device_read_bandwidth: bad argument"); return PB_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); pb::set_error("no CUDA device is available"); return PB_ERR_NO_DEVICE; }
+  CU(cudaSetDevice(device));
+  DBuf<uint4> buf;
+  DBuf<ull> sink;
+  const uint64_t n = bytes / sizeof(uint4);
+  CU(buf.ensure(n));
+  CU(sink.ensure(1));
+  CU(cudaMemset(buf.p, 1, n * sizeof(uint4)));
+  CU(cudaMemset(sink.p, 0, sizeof(ull)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int grid = g_sm_count(device) * 8;
+  read_bw_kernel<<<grid, 256>>>(buf.p, n, 1, sink.p);
+  CU(cudaEventRecord(e0));
+  read_bw_kernel<<<grid, 256>>>(buf.p, n, iters, sink.p);
+  CU(cudaEventRecord(e1));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU(cudaGetLastError());
+  *gb_per_s = (double)n * sizeof(uint4) * iters / (ms * 1e-3) / 1e9;
+  return PB_OK;
+}
+
+int pb_index_device_layout(pb_index* ix, pb_device_layout* out) {
+  if (!ix || !out) { pb::set_error("pb_index_device_layout: null argument"); return PB_ERR_INVALID; }
+  std::memset(out, 0, sizeof(*out));
+  out->narrow = ix->narrow ? 1u : 0u;
+  out->bytes_per_row = ix->narrow ? 4u + 2u * ix->F : 4u + 8u * ix->F;
+  for (uint32_t f = 0; f < ix->F; ++f) out->fl_bits[f] = ix->fl_bits[f];
+  out->posting_bytes = (ix->n_rows_padded / TILE_ROWS) * (uint64_t)ix->tile_words * 4ull;
   return PB_OK;
 }
 

@@ -291,6 +291,14 @@ class Index:
         capi.check(self._L.pb_index_last_stats(self._ix, C.byref(s)))
         return s.as_dict()
 
+    def device_layout(self) -> dict:
+        """How the posting columns are held in HBM (pb_device_layout): narrow u16 codes or u32 columns."""
+        self.sync_device()
+        d = capi.DeviceLayout()
+        capi.check(self._L.pb_index_device_layout(self._ix, C.byref(d)))
+        return {"narrow": bool(d.narrow), "bytes_per_row": int(d.bytes_per_row), "posting_bytes": int(d.posting_bytes),
+                "fl_bits": [int(x) for x in d.fl_bits][: self.fields_num]}
+
     def term_df_live(self) -> np.ndarray:
         self.sync_device()
         im = self.flatten()

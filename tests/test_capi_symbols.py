@@ -33,8 +33,8 @@ def test_struct_sizes_match_header():
     #include <stdio.h>
     #include "probly_b200.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pb_doc_tokens), sizeof(pb_builder_info), sizeof(pb_index_image),
-             sizeof(pb_query_batch_desc), sizeof(pb_query_results), sizeof(pb_batch_stats));
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(pb_doc_tokens), sizeof(pb_builder_info), sizeof(pb_index_image),
+             sizeof(pb_query_batch_desc), sizeof(pb_query_results), sizeof(pb_batch_stats), sizeof(pb_device_layout));
       return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -42,7 +42,8 @@ def test_struct_sizes_match_header():
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    mirrors = [capi.DocTokens, capi.BuilderInfo, capi.IndexImage, capi.QueryBatchDesc, capi.QueryResults, capi.BatchStats]
+    mirrors = [capi.DocTokens, capi.BuilderInfo, capi.IndexImage, capi.QueryBatchDesc, capi.QueryResults, capi.BatchStats,
+               capi.DeviceLayout]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 
