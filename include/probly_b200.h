@@ -135,6 +135,18 @@ typedef struct pb_index_image {
 } pb_index_image;
 int pb_builder_flatten(pb_builder* b, pb_index_image* out);
 
+/* On-disk / wire format of an image (the reference has no serialisation at all: no serde, the index
+ * lives only in RAM — SURVEY §5, §8f-2).  One file = header + section table + 64-byte aligned
+ * sections + FNV-1a checksum (layout: csrc/image_io.cpp).  pb_image_load validates magic, section
+ * sizes against the header scalars and the checksum; the returned handle owns the buffer the
+ * image's pointers point into, so a serving process needs no pb_builder:
+ *   pb_image_load(path, &f); pb_index_create(pb_image_file_image(f), dev, &ix); pb_image_file_free(f); */
+typedef struct pb_image_file pb_image_file;
+int pb_image_save(const pb_index_image* image, const char* path);
+int pb_image_load(const char* path, pb_image_file** out);
+const pb_index_image* pb_image_file_image(const pb_image_file* f);
+void pb_image_file_free(pb_image_file* f);
+
 /* ------------------------------------------------------------------------------------------
  * Device image
  * ---------------------------------------------------------------------------------------- */

@@ -30,14 +30,14 @@ def build_variant(name: str, defs) -> str:
     """Tuning helper: the same library with extra -D flags, as _lib/libprobly_b200_<name>.so."""
     os.makedirs(OUT, exist_ok=True)
     out = os.path.join(OUT, f"libprobly_b200_{name}.so")
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "builder.cpp", "common.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "builder.cpp", "common.cpp", "image_io.cpp")]
     subprocess.check_call(["nvcc"] + NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-o", out] + srcs)
     return out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "builder.cpp", "common.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "builder.cpp", "common.cpp", "image_io.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "common.hpp")] + [
         os.path.join(HERE, "..", "include", "probly_b200.h")]
     if force or _newer(LIB, deps):

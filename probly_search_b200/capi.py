@@ -89,7 +89,8 @@ EXPORTS = [
     "pb_builder_create", "pb_builder_destroy", "pb_builder_add_document", "pb_builder_add_documents",
     "pb_builder_remove_document", "pb_builder_vacuum", "pb_builder_get_info", "pb_builder_flatten",
     "pb_device_count", "pb_index_create", "pb_index_set_live_state", "pb_index_destroy",
-    "pb_index_expand_term", "pb_index_term_df_live", "pb_index_device_layout", "pb_device_read_bandwidth", "pb_query_batch", "pb_batch_create", "pb_batch_run",
+    "pb_index_expand_term", "pb_index_term_df_live", "pb_index_device_layout", "pb_device_read_bandwidth",
+    "pb_image_save", "pb_image_load", "pb_image_file_image", "pb_image_file_free", "pb_query_batch", "pb_batch_create", "pb_batch_run",
     "pb_batch_fetch", "pb_batch_destroy", "pb_batch_device_results", "pb_batch_get_stats", "pb_index_last_stats", "pb_query_full",
     "pb_host_alloc", "pb_host_free", "pb_last_error", "pb_version",
 ]
@@ -132,6 +133,10 @@ def lib() -> C.CDLL:
         "pb_index_expand_term": (i32, [vp, vp, u64, vp, u64, P(u64), P(u64)]),
         "pb_index_term_df_live": (i32, [vp, vp, u64]),
         "pb_index_device_layout": (i32, [vp, vp]),
+        "pb_image_save": (i32, [vp, C.c_char_p]),
+        "pb_image_load": (i32, [C.c_char_p, vp]),
+        "pb_image_file_image": (vp, [vp]),
+        "pb_image_file_free": (None, [vp]),
         "pb_device_read_bandwidth": (i32, [i32, u64, C.c_uint32, vp]),
         "pb_query_batch": (i32, [vp, P(QueryBatchDesc), P(QueryResults)]),
         "pb_batch_create": (i32, [vp, P(QueryBatchDesc), P(vp)]),
@@ -158,3 +163,7 @@ def lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != PB_OK:
         raise ProblyError(rc, lib().pb_last_error().decode("utf-8", "replace"))
+
+
+def last_error() -> str:
+    return lib().pb_last_error().decode("utf-8", "replace")

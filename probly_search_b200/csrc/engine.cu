@@ -433,7 +433,11 @@ ScorePlan score_plan(const pb_batch* b, uint32_t tab_total) {
   while (sh > 0 && (((size_t)tab_total * 8) << sh) > budget) --sh;
   sp.rep_shift = sh;
   sp.smem = (((size_t)tab_total * 8) << sh) + 128;
-  sp.threads = sp.smem <= (72u << 10) ? 256 : sp.smem <= (110u << 10) ? 384 : SCORE_MAX_THREADS;
+  // smallest CTA whose copies still add up to SCORE_MAX_THREADS resident threads per SM within the budget
+  sp.threads = SCORE_MAX_THREADS;
+  for (int t : {256, SCORE_MAX_THREADS / 2}) {
+    if (SCORE_MAX_THREADS % t == 0 && (size_t)(SCORE_MAX_THREADS / t) * (sp.smem + 1024) <= budget) { sp.threads = t; break; }
+  }
   (void)b;
   return sp;
 }

@@ -1091,9 +1091,12 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
 }
 
 // CTA shape of the scoring kernel: no barrier after the table is loaded, so a CTA is just a bag of
-// warps.  The host picks (threads per CTA, CTAs per SM) so that ~24 warps are resident per SM
-// whatever the shared-memory table costs: 3 x 256, 2 x 384 or 1 x 768 threads.
-constexpr int SCORE_MAX_THREADS = 768;
+// warps.  The host picks (threads per CTA, CTAs per SM) so that 32 warps are resident per SM
+// whatever the shared-memory table costs: 4 x 256, 2 x 512 or 1 x 1024 threads (64 registers per thread).
+#ifndef PB_SCORE_MAX_THREADS
+#define PB_SCORE_MAX_THREADS 1024
+#endif
+constexpr int SCORE_MAX_THREADS = PB_SCORE_MAX_THREADS;
 
 template <int F, int SCORER, bool GMODE, bool NARROW>
 __global__ void __launch_bounds__(SCORE_MAX_THREADS, 1) score_kernel(const __grid_constant__ ScoreParams P) {

@@ -9,6 +9,7 @@ through the C ABI (include/probly_b200.h); there is no Python implementation of 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Any, Callable, Hashable, List, Optional, Sequence
 
@@ -111,8 +112,36 @@ class Index:
         self._id_to_key: list = []
         self._ord_to_id: Optional[np.ndarray] = None
 
+    # -- on-disk image (the reference has no serialisation) -----------------------
+    def save_image(self, path: str) -> None:
+        """Writes the flattened image (what pb_index_create uploads) to `path` (csrc/image_io.cpp)."""
+        im = self.flatten()
+        capi.check(self._L.pb_image_save(C.byref(im), os.fsencode(path)))
+
+    @classmethod
+    def load_image(cls, path: str, device: int = 0) -> "Index":
+        """A query-only Index served straight from an image file: no host builder exists, mutation
+        raises, result keys are the u64 key ids stored in the image."""
+        self = cls.__new__(cls)
+        self._L = capi.lib()
+        h = C.c_void_p()
+        capi.check(self._L.pb_image_load(os.fsencode(path), C.byref(h)))
+        self._image_file = h
+        self._b = None
+        self._ix = None
+        self.device = device
+        im = C.cast(self._L.pb_image_file_image(h), C.POINTER(capi.IndexImage)).contents
+        self.fields_num = int(im.num_fields)
+        self._image_dirty, self._live_dirty = True, False
+        self._key_to_id, self._id_to_key, self._ord_to_id = {}, [], None
+        self._flat_keys = True
+        return self
+
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self) -> None:
+        if getattr(self, "_image_file", None):
+            self._L.pb_image_file_free(self._image_file)
+            self._image_file = None
         if getattr(self, "_ix", None):
             self._L.pb_index_destroy(self._ix)
             self._ix = None
@@ -152,7 +181,7 @@ class Index:
         vc = np.asarray(vcount + [0], dtype=np.uint32)
         fc = np.asarray(fcount, dtype=np.uint32)
         d = capi.DocTokens(buf.ctypes.data, off.ctypes.data, vc.ctypes.data, fc.ctypes.data)
-        capi.check(self._L.pb_builder_add_document(self._b, self._key_id(key), C.byref(d)))
+        capi.check(self._L.pb_builder_add_document(self._require_builder(), self._key_id(key), C.byref(d)))
         self._image_dirty = True
 
     def add_documents_flat(self, keys: np.ndarray, tok_bytes: np.ndarray, tok_off: np.ndarray,
@@ -162,7 +191,7 @@ class Index:
         if self._id_to_key:
             raise ValueError("add_documents_flat cannot be mixed with add_document on one index")
         self._flat_keys = True
-        capi.check(self._L.pb_builder_add_documents(self._b, len(keys), keys.ctypes.data, tok_bytes.ctypes.data,
+        capi.check(self._L.pb_builder_add_documents(self._require_builder(), len(keys), keys.ctypes.data, tok_bytes.ctypes.data,
                                                     tok_off.ctypes.data, field_tok_count.ctypes.data))
         self._image_dirty = True
 
@@ -171,23 +200,30 @@ class Index:
         kid = key if getattr(self, "_flat_keys", False) else self._key_to_id.get(key)
         if kid is None:
             return
-        capi.check(self._L.pb_builder_remove_document(self._b, int(kid)))
+        capi.check(self._L.pb_builder_remove_document(self._require_builder(), int(kid)))
         self._live_dirty = True
 
     def vacuum(self) -> None:
         """src/index.rs:194-199"""
-        capi.check(self._L.pb_builder_vacuum(self._b))
+        capi.check(self._L.pb_builder_vacuum(self._require_builder()))
         self._image_dirty = True
 
     def info(self) -> capi.BuilderInfo:
         out = capi.BuilderInfo()
-        capi.check(self._L.pb_builder_get_info(self._b, C.byref(out)))
+        capi.check(self._L.pb_builder_get_info(self._require_builder(), C.byref(out)))
         return out
 
     def flatten(self) -> capi.IndexImage:
+        if getattr(self, "_image_file", None):
+            return C.cast(self._L.pb_image_file_image(self._image_file), C.POINTER(capi.IndexImage)).contents
         im = capi.IndexImage()
-        capi.check(self._L.pb_builder_flatten(self._b, C.byref(im)))
+        capi.check(self._L.pb_builder_flatten(self._require_builder(), C.byref(im)))
         return im
+
+    def _require_builder(self):
+        if self._b is None:
+            raise capi.ProblyError(capi.PB_ERR_UNSUPPORTED, "this Index was loaded from an image file and cannot be mutated")
+        return self._b
 
     # -- device image --------------------------------------------------------------------------
     def sync_device(self) -> None:

@@ -198,3 +198,83 @@ def test_error_paths_do_not_abort():
     assert e.value.code == capi.PB_ERR_UNSUPPORTED
     with pytest.raises(capi.ProblyError):
         ix.query_batch_flat(FlatQueries.from_strings(["a"], TOK), score.bm25.new(), [float("nan")], top_k=1)
+
+
+# ---- device posting layouts: results must not depend on the layout ------------
+@pytest.mark.parametrize("layout", ["wide", "auto"])
+@pytest.mark.parametrize("seed", [3, 6])
+def test_random_corpora_both_layouts(monkeypatch, layout, seed):
+    monkeypatch.setenv("PB_POSTING_LAYOUT", layout)
+    rng = random.Random(7000 + seed)
+    n_fields = [1, 2, 3, 4][seed % 4]
+    docs = H.random_corpus(rng, rng.randint(20, 60), n_fields, multi_value=True)
+    ix, o = both(docs, n_fields)
+    queries = [H.random_query(rng) for _ in range(30)] + ["a", "ab abc abcd a"]
+    compare_queries(ix, o, queries, [1.0] * n_fields, f"layout={layout} seed={seed}")
+    compare_queries(ix, o, queries[:12], [rng.choice([2.0, 0.5, -1.0]) for _ in range(n_fields)], f"layout={layout} boosts")
+    assert ix.device_layout()["narrow"] == (layout == "auto")
+    for k, _ in docs[::3]:
+        ix.remove_document(k)
+        o.remove_document(k)
+    compare_queries(ix, o, queries[:15], [1.0] * n_fields, f"layout={layout} removed")
+
+
+@pytest.mark.parametrize("layout", ["wide", "auto"])
+@pytest.mark.parametrize("cfg_name,n_docs,vocab,n_queries,removed", [
+    ("cfg1", 30_000, 1 << 12, 300, False),
+    ("cfg2", 20_000, 1 << 12, 50, False),
+    ("cfg4", 30_000, 1 << 12, 200, True),
+])
+def test_scaled_configs_both_layouts(monkeypatch, layout, cfg_name, n_docs, vocab, n_queries, removed):
+    monkeypatch.setenv("PB_POSTING_LAYOUT", layout)
+    cfg, ix, o, fq, scorer = _scaled(cfg_name, n_docs, vocab, n_queries, removed)
+    batch = DeviceBatch(ix, fq, CALC[scorer](), cfg.boosts, top_k=10)
+    batch.run()
+    got = batch.fetch()
+    assert ix.device_layout()["narrow"] == (layout == "auto")
+    assert ix.device_layout()["bytes_per_row"] == (4 + 2 * cfg.n_fields if layout == "auto" else 4 + 8 * cfg.n_fields)
+    exp = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, scorer, cfg.boosts, 10)
+    np.testing.assert_array_equal(got.n_results, exp["n_results"])
+    np.testing.assert_array_equal(got.doc_digest, exp["doc_digest"])
+    np.testing.assert_array_equal(got.score_digest, exp["score_digest"])
+    for q in range(fq.n_queries):
+        n = int(got.topk_n[q])
+        np.testing.assert_array_equal(got.topk_doc[q, :n], exp["topk_key"][q, :n].astype(np.uint32))
+        np.testing.assert_array_equal(got.topk_score[q, :n], exp["topk_score"][q, :n])
+
+
+def test_long_fields_fall_back_to_wide_layout():
+    """A field of 300 tokens / a tf of 300 does not fit a u16 (tf, fl) code: the device keeps u32 columns
+    (and the BM25 table no longer covers every (tf, fl): the exact division path runs)."""
+    rng = random.Random(99)
+    words = ["alpha", "beta", "gamma", "delta", "al", "alp", "be"]
+    docs = []
+    for k in range(40):
+        n0 = rng.choice([3, 10, 300, 700])
+        f0 = " ".join(rng.choice(words) for _ in range(n0))
+        f1 = " ".join(["alpha"] * rng.choice([1, 2, 300])) + " " + " ".join(rng.choice(words) for _ in range(5))
+        docs.append((k, [[f0], [f1]]))
+    ix, o = both(docs, 2)
+    compare_queries(ix, o, ["alpha", "al", "be gamma", "a", "alpha alpha beta", "delta alp"], [1.0, 1.0], "long fields")
+    compare_queries(ix, o, ["alpha", "al be"], [0.5, 2.0], "long fields boosts")
+    assert ix.device_layout()["narrow"] is False
+
+
+def test_index_served_from_an_image_file(tmp_path):
+    """save the flattened image, load it in a builder-less Index, same results bit for bit
+    (pre-vacuum removed docs included: the live state travels in the image)."""
+    cfg, ix, o, fq, scorer = _scaled("cfg4", 20_000, 1 << 12, 150, removed=True)
+    p = str(tmp_path / "cfg4.pbimg")
+    ix.save_image(p)
+    ld = Index.load_image(p)
+    a = ix.query_batch_flat(fq, CALC[scorer](), cfg.boosts, top_k=10)
+    b = ld.query_batch_flat(fq, CALC[scorer](), cfg.boosts, top_k=10)
+    exp = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, scorer, cfg.boosts, 10)
+    for got in (a, b):
+        np.testing.assert_array_equal(got.n_results, exp["n_results"])
+        np.testing.assert_array_equal(got.doc_digest, exp["doc_digest"])
+        np.testing.assert_array_equal(got.score_digest, exp["score_digest"])
+    np.testing.assert_array_equal(a.topk_doc, b.topk_doc)
+    np.testing.assert_array_equal(a.topk_score, b.topk_score)
+    assert ld.expand_term("a") == ix.expand_term("a")
+    ld.close()
