@@ -113,6 +113,9 @@ struct pb_index {
   DBuf<uint32_t> term_byte_len, post_blocks, removed, live_prefix, term_live_rows;
   DBuf<uint64_t> term_df_live, liverows_prefix;
   DBuf<double> term_idf, eb;
+  DBuf<uint2> dir;              // rank directories of the dense posting lists (IndexView::dir)
+  DBuf<uint32_t> term_dir;
+  uint32_t dir_words = 0, n_dense = 0;
   // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
   std::vector<uint32_t> h_node_parent, h_node_char, h_term_node;
   std::vector<uint64_t> h_term_row_begin, h_df_live;
@@ -131,6 +134,7 @@ struct pb_index {
     v.removed = removed.p;
     v.term_df_live = term_df_live.p; v.term_live_rows = term_live_rows.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
     v.term_idf = term_idf.p; v.eb = eb.p;
+    v.dir = dir.p; v.term_dir = term_dir.p; v.dir_words = dir_words;
     v.n_terms = (uint32_t)n_terms; v.n_docs = (uint32_t)n_docs; v.num_fields = F;
     v.has_removed = n_removed ? 1u : 0u;
     return v;
@@ -978,6 +982,30 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
               codes[f * TILE_ROWS + r] = (uint16_t)((src[(1 + f) * TILE_ROWS + r] << ix->fl_bits[f]) | src[(1 + ix->F + f) * TILE_ROWS + r]);
         }
         CU(upload(ix->post_blocks, nb.data(), nb.size(), 0));
+      }
+    }
+    // rank directories of the dense lists (>= n_docs / 32 rows, capped at 1 GB): built on the device
+    {
+      std::vector<uint32_t> tdir(im->n_terms + 1, 0u), dense;
+      ix->dir_words = (uint32_t)((im->n_docs + 31) / 32 + 1);
+      uint64_t min_rows = std::max<uint64_t>(4096, im->n_docs / 32);
+      if (const char* e = std::getenv("PB_DIR_MIN_ROWS")) min_rows = std::max<long long>(1, atoll(e));   // tests: directories for every list
+      const uint64_t max_dense = (1ull << 30) / ((uint64_t)ix->dir_words * sizeof(uint2));
+      for (uint64_t t = 0; t < im->n_terms && dense.size() < max_dense; ++t)
+        if (im->term_row_begin[t + 1] - im->term_row_begin[t] >= min_rows) { dense.push_back((uint32_t)t); tdir[t] = (uint32_t)dense.size(); }
+      ix->n_dense = (uint32_t)dense.size();
+      CU(upload(ix->term_dir, tdir.data(), tdir.size()));
+      CU(ix->dir.ensure((size_t)ix->n_dense * ix->dir_words + 1));
+      if (ix->n_dense) {
+        DBuf<uint32_t> d_dense;
+        CU(upload(d_dense, dense.data(), dense.size()));
+        CU(cudaMemset(ix->dir.p, 0, (size_t)ix->n_dense * ix->dir_words * sizeof(uint2)));
+        IndexView v = ix->view();
+        dir_bits_kernel<<<dim3(64, std::min<uint32_t>(ix->n_dense, 1024)), 256>>>(v, d_dense.p, ix->n_dense, ix->dir.p);
+        CU(cudaGetLastError());
+        dir_rank_kernel<<<ix->n_dense, 1024>>>(ix->dir_words, ix->dir.p);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
       }
     }
     ix->h_node_parent.assign(im->node_parent, im->node_parent + im->n_nodes);

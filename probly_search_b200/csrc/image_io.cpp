@@ -84,7 +84,7 @@ int pb_image_save(const pb_index_image* im, const char* path) {
     sc.version = im->version; sc.num_fields = im->num_fields;
     sc.n_nodes = im->n_nodes; sc.n_edges = im->n_edges; sc.n_terms = im->n_terms; sc.n_rows = im->n_rows;
     sc.n_rows_padded = im->n_rows_padded; sc.n_docs = im->n_docs; sc.max_term_bytes = im->max_term_bytes;
-    for (int f = 0; f < PB_MAX_FIELDS; ++f) { sc.max_tf[f] = im->max_tf[f]; sc.max_fl[f] = im->max_fl[f]; sc.field_avg[f] = im->field_avg[f]; }
+    for (uint32_t f = 0; f < PB_MAX_FIELDS; ++f) { sc.max_tf[f] = im->max_tf[f]; sc.max_fl[f] = im->max_fl[f]; sc.field_avg[f] = im->field_avg[f]; }
     sc.n_removed = im->n_removed; sc.n_live_docs = im->n_live_docs;
     const uint64_t header_bytes = align64(16 + sizeof(Scalars) + N_SECTIONS * 16 + 8);
     uint64_t table[N_SECTIONS][2];
@@ -149,7 +149,7 @@ int pb_image_load(const char* path, pb_image_file** out) {
     im.version = sc.version; im.num_fields = sc.num_fields;
     im.n_nodes = sc.n_nodes; im.n_edges = sc.n_edges; im.n_terms = sc.n_terms; im.n_rows = sc.n_rows;
     im.n_rows_padded = sc.n_rows_padded; im.n_docs = sc.n_docs; im.max_term_bytes = sc.max_term_bytes;
-    for (int x = 0; x < PB_MAX_FIELDS; ++x) { im.max_tf[x] = sc.max_tf[x]; im.max_fl[x] = sc.max_fl[x]; im.field_avg[x] = sc.field_avg[x]; }
+    for (uint32_t x = 0; x < PB_MAX_FIELDS; ++x) { im.max_tf[x] = sc.max_tf[x]; im.max_fl[x] = sc.max_fl[x]; im.field_avg[x] = sc.field_avg[x]; }
     im.n_removed = sc.n_removed; im.n_live_docs = sc.n_live_docs;
     // the section sizes the scalars imply must be the sizes on file
     Section expect[N_SECTIONS];

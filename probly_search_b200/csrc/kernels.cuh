@@ -83,6 +83,13 @@ struct IndexView {
   const uint64_t* liverows_prefix;// [n_terms+1] rows of live terms before t
   const double* term_idf;         // bm25.rs:56, host libm
   const double* eb;               // bm25.rs:45-53 by byte-length delta, host libm
+  // Rank directory of the DENSE posting lists (rows >= n_docs / 32), built on the device at
+  // pb_index_create: per 32-doc word {rows of the list before this word, bits of the docs present}.
+  // row of doc d in the list = row_begin + dir.x + popc(dir.y & ((1 << (d & 31)) - 1)): the marking
+  // pass finds a secondary doc in a dense primary list with ONE load instead of a binary search.
+  const uint2* dir;               // [n_dense][dir_words]
+  const uint32_t* term_dir;       // [n_terms] 1 + index of the term's directory, 0 = none
+  uint32_t dir_words;
   uint32_t n_terms;
   uint32_t n_docs;
   uint32_t num_fields;
@@ -467,6 +474,49 @@ __global__ void live_df_kernel(IndexView ix, unsigned long long* __restrict__ df
   }
 }
 
+// Rank directory build (see IndexView::dir).  Pass 1: one warp-strided walk over the rows of every
+// dense term sets the doc bits.  Pass 2: one CTA per dense term turns the per-word popcounts into
+// exclusive prefix sums.
+__global__ void dir_bits_kernel(IndexView ix, const uint32_t* __restrict__ dense_terms, uint32_t n_dense, uint2* __restrict__ dir) {
+  for (uint32_t i = blockIdx.y; i < n_dense; i += gridDim.y) {
+    const uint32_t t = dense_terms[i];
+    const uint64_t a = ix.term_row_begin[t], b = ix.term_row_begin[t + 1];
+    uint2* d = dir + (size_t)i * ix.dir_words;
+    for (uint64_t r = a + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < b; r += (uint64_t)gridDim.x * blockDim.x) {
+      const uint32_t doc = row_doc(ix, r);
+      atomicOr(&d[doc >> 5].y, 1u << (doc & 31));
+    }
+  }
+}
+__global__ void __launch_bounds__(1024) dir_rank_kernel(uint32_t dir_words, uint2* __restrict__ dir) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_base;
+  uint2* d = dir + (size_t)blockIdx.x * dir_words;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (uint32_t w0 = 0; w0 < dir_words; w0 += blockDim.x) {
+    const uint32_t w = w0 + threadIdx.x;
+    const uint32_t c = w < dir_words ? __popc(d[w].y) : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t v = s_warp[threadIdx.x], x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, x, o); if (threadIdx.x >= o) x += u; }
+      s_warp[threadIdx.x] = x - v;              // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (w < dir_words) d[w].x = base + s_warp[threadIdx.x >> 5] + incl - c;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_base = base + s_warp[threadIdx.x >> 5] + incl;
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Planning
 // ------------------------------------------------------------------------------------------
@@ -620,7 +670,7 @@ __global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const uns
       bound = 2ull * secondary;
       // row mask: 4 words per tile the primary list touches
       const unsigned long long a = seg_g[idx].row_begin, e = a + seg_g[idx].n_rows;
-      bmw = 4ull * ((e + TILE_ROWS - 1) / TILE_ROWS - a / TILE_ROWS) + 4ull;
+      bmw = 4ull * ((e + TILE_ROWS - 1) / TILE_ROWS - a / TILE_ROWS) + 12ull;     // + pads: the scoring loop reads masks 2 tiles ahead
     }
     // doc-range bins of width 2^shift sized for ~8 records each (a warp window holds 32)
     const unsigned long long n_docs_pow = 1ull << doc_bits;
@@ -702,9 +752,12 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
       const uint64_t abs0 = sg.row_begin / TILE_ROWS;
       const uint64_t rend = sg.row_begin + sg.n_rows;
       uint64_t pbeg = 0, pend = 0, pabs0 = 0;
+      const uint2* pdir = nullptr;             // rank directory of the primary list, when it is a dense one
       if (!exact) {
         const Seg pr = P.segs[0xFFFFFFFFu - (uint32_t)(P.q_prim[sg.q] & 0xFFFFFFFFull)];
         pbeg = pr.row_begin; pend = pbeg + pr.n_rows; pabs0 = pbeg / TILE_ROWS;
+        const uint32_t di = P.ix.term_dir[pr.term];
+        if (di) pdir = P.ix.dir + (size_t)(di - 1) * P.ix.dir_words;
       }
       if (exact) xtiles += tend - t;
       for (; t < tend; ++t) {
@@ -730,11 +783,27 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
             }
           }
         } else {
-          // four lower-bound searches of the lane's docs in the primary list, in lockstep
+          // position of the lane's docs in the primary list: one directory load each for a dense list,
+          // otherwise four lower-bound searches in lockstep
           uint64_t lo[4], hi[4];
+          bool found[4] = {false, false, false, false};
+          if (pdir) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { lo[j] = pbeg; hi[j] = inr[j] ? pend : pbeg; }
-          while (true) {
+            for (int j = 0; j < 4; ++j) {
+              lo[j] = pend;
+              if (inr[j]) {
+                const uint2 e = __ldg(&pdir[dv[j] >> 5]);
+                const uint32_t bit = 1u << (dv[j] & 31);
+                found[j] = (e.y & bit) != 0u;
+                lo[j] = pbeg + e.x + __popc(e.y & (bit - 1u));
+              }
+              hi[j] = lo[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { lo[j] = pbeg; hi[j] = inr[j] ? pend : pbeg; }
+          }
+          while (!pdir) {
             bool more = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -751,7 +820,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mark_kernel(const __grid_constant
             if (!inr[j]) continue;
             uint32_t inc = 1u;
             const uint64_t r = lo[j];
-            if (r < pend && row_doc(P.ix, r) == dv[j]) {
+            if (pdir ? found[j] : (r < pend && row_doc(P.ix, r) == dv[j])) {
               const uint32_t bit = 1u << (r & 31);
               const uint32_t old = atomicOr(&sm[(r / TILE_ROWS - pabs0) * 4 + ((r % TILE_ROWS) >> 5)], bit);
               inc = (old & bit) ? 1u : 2u;
@@ -913,8 +982,11 @@ __device__ __forceinline__ uint2 ldg_stream_u64(const uint32_t* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
-__device__ __forceinline__ uint32_t* rowmask_word(const SegCtx& C, uint64_t tile_row, int lane) {
-  return C.rowmask + (tile_row / TILE_ROWS - C.rbeg / TILE_ROWS) * 4 + (lane >> 3);
+__device__ __forceinline__ uint32_t rel_tile(const SegCtx& C, uint64_t tile_row) {
+  return (uint32_t)(tile_row / TILE_ROWS - C.rbeg / TILE_ROWS);
+}
+__device__ __forceinline__ uint32_t* rowmask_word(const SegCtx& C, uint32_t ti, int lane) {
+  return C.rowmask + (size_t)ti * 4 + (lane >> 3);
 }
 template <int F>
 __device__ __forceinline__ void load_cols(TileRegs<F, false>& R, const uint32_t* base, int lane) {
@@ -939,8 +1011,9 @@ template <int F, bool GMODE, bool NARROW>
 __device__ __forceinline__ void load_tile(const SegCtx& C, const uint32_t* base, const uint32_t* maskp, int lane, TileRegs<F, NARROW>& R) {
   // one contiguous block per tile: a single base address, immediate column offsets
   R.mw = 0;
-  if (GMODE && C.mode == MODE_PRIMARY) {
+  if (GMODE && maskp != nullptr) {
     // the address does not depend on posting data: the mask word travels together with the tile
+    // (maskp is null when the tile summary says the tile diverts nothing)
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(R.mw) : "l"(maskp));
   }
   R.dq = ldg_stream(base + lane * 4);
@@ -949,7 +1022,7 @@ __device__ __forceinline__ void load_tile(const SegCtx& C, const uint32_t* base,
 
 template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE, bool NARROW>
 __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
-                                             const TileRegs<F, NARROW>& R, uint64_t tile_row, uint32_t* maskp, int lane,
+                                             const TileRegs<F, NARROW>& R, uint64_t tile_row, uint32_t ti, int lane,
                                              WarpAcc& acc, uint32_t& st_div) {
   const uint4 dq = R.dq;
   const uint32_t dv[4] = {dq.x, dq.y, dq.z, dq.w};
@@ -999,7 +1072,7 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
     if (C.mode == MODE_PRIMARY) {
       dmask = (R.mw >> ((lane & 7) * 4)) & valid;
       // consumed: the pool is clean again for the next round (only the warp that scores the tile clears it)
-      if (R.mw != 0u && (lane & 7) == 0) *maskp = 0u;
+      if (R.mw != 0u && (lane & 7) == 0) *rowmask_word(C, ti, lane) = 0u;
     } else if (C.mode != MODE_SECONDARY) {
       dmask = 0;
       bool maybe = true;
@@ -1021,6 +1094,7 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
     some &= ~dmask;
     if (dmask) {
       // one fat record per diverted row, written straight into the doc-range bin of the query
+      // (overlapping the four cursor atomics of a lane was measured: no gain, more registers)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if ((dmask >> j) & 1u) {
@@ -1050,9 +1124,10 @@ template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE, bool 
 __device__ __forceinline__ void process_tile(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                              uint64_t tile_row, int lane, WarpAcc& acc, uint32_t& st_div) {
   TileRegs<F, NARROW> R;
-  uint32_t* maskp = (GMODE && C.mode == MODE_PRIMARY) ? rowmask_word(C, tile_row, lane) : nullptr;
+  const uint32_t ti = (GMODE && C.mode == MODE_PRIMARY) ? rel_tile(C, tile_row) : 0u;
+  uint32_t* maskp = (GMODE && C.mode == MODE_PRIMARY) ? rowmask_word(C, ti, lane) : nullptr;
   load_tile<F, GMODE, NARROW>(C, tile_base<F, NARROW>(P, tile_row), maskp, lane, R);
-  compute_tile<F, SCORER, GMODE, EDGE, FAST, SIMPLE, NARROW>(P, s_tab, C, R, tile_row, maskp, lane, acc, st_div);
+  compute_tile<F, SCORER, GMODE, EDGE, FAST, SIMPLE, NARROW>(P, s_tab, C, R, tile_row, ti, lane, acc, st_div);
 }
 
 // Interior tiles of one segment (every row belongs to the segment).  In the narrow layout a tile is
@@ -1067,22 +1142,37 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
   if (NARROW) {
     if (n_tiles == 0) return;
     const uint32_t* base = tile_base<F, NARROW>(P, tile_row);
-    uint32_t* maskp = (GMODE && C.mode == MODE_PRIMARY) ? rowmask_word(C, tile_row, lane) : nullptr;
+    const bool primary = GMODE && C.mode == MODE_PRIMARY;
+    uint32_t ti = primary ? rel_tile(C, tile_row) : 0u;
+    // Row-mask words of a primary list come from a multi-GB pool (DRAM latency): they are requested TWO
+    // tiles ahead, the posting tiles (mostly L2 hits) one tile ahead.
+    const uint32_t* maskp = primary ? rowmask_word(C, ti, lane) : nullptr;
+    auto ld_mask = [&](const uint32_t* p) -> uint32_t {
+      uint32_t v = 0;
+      if (primary) asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+      return v;
+    };
     TileRegs<F, NARROW> cur;
-    load_tile<F, GMODE, NARROW>(C, base, maskp, lane, cur);
+    load_tile<F, GMODE, NARROW>(C, base, nullptr, lane, cur);
+    cur.mw = ld_mask(maskp);
+    uint32_t mw1 = ld_mask(maskp + 4);               // mask of tile i + 1
 #pragma unroll 2
     for (uint32_t i = 0; i < n_tiles; ++i) {
       TileRegs<F, NARROW> nxt;
-      load_tile<F, GMODE, NARROW>(C, base + TileGeom<F, NARROW>::WORDS, maskp + 4, lane, nxt);
+      load_tile<F, GMODE, NARROW>(C, base + TileGeom<F, NARROW>::WORDS, nullptr, lane, nxt);
+      const uint32_t mw2 = ld_mask(maskp + 8);       // mask of tile i + 2
       // a primary-list tile whose row-mask bits are all clear diverts nothing: score it exactly like a
       // single-list tile (the common case: ~93 % of the tiles of the cfg 1 batch)
-      if (GMODE && C.mode == MODE_PRIMARY && !__any_sync(0xffffffffu, cur.mw != 0u))
-        compute_tile<F, SCORER, false, false, FAST, SIMPLE, NARROW>(P, s_tab, C, cur, 0, nullptr, lane, acc, st_div);
+      if (primary && !__any_sync(0xffffffffu, cur.mw != 0u))
+        compute_tile<F, SCORER, false, false, FAST, SIMPLE, NARROW>(P, s_tab, C, cur, 0, 0u, lane, acc, st_div);
       else
-        compute_tile<F, SCORER, GMODE, false, FAST, SIMPLE, NARROW>(P, s_tab, C, cur, 0, maskp, lane, acc, st_div);
+        compute_tile<F, SCORER, GMODE, false, FAST, SIMPLE, NARROW>(P, s_tab, C, cur, 0, ti, lane, acc, st_div);
       cur = nxt;
+      cur.mw = mw1;
+      mw1 = mw2;
       base += TileGeom<F, NARROW>::WORDS;
       maskp += 4;
+      ++ti;
     }
   } else {
     for (uint32_t i = 0; i < n_tiles; ++i, tile_row += TILE_ROWS)
@@ -1091,10 +1181,11 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
 }
 
 // CTA shape of the scoring kernel: no barrier after the table is loaded, so a CTA is just a bag of
-// warps.  The host picks (threads per CTA, CTAs per SM) so that 32 warps are resident per SM
-// whatever the shared-memory table costs: 4 x 256, 2 x 512 or 1 x 1024 threads (64 registers per thread).
+// warps.  The host picks (threads per CTA, CTAs per SM) so that 24 warps are resident per SM
+// whatever the shared-memory table costs: 3 x 256, 2 x 384 or 1 x 768 threads (80 registers per thread;
+// 32 warps at 64 registers measured 5 % slower in an alternating A/B on one box: spills reach the loop).
 #ifndef PB_SCORE_MAX_THREADS
-#define PB_SCORE_MAX_THREADS 1024
+#define PB_SCORE_MAX_THREADS 768
 #endif
 constexpr int SCORE_MAX_THREADS = PB_SCORE_MAX_THREADS;
 

@@ -243,6 +243,23 @@ def test_scaled_configs_both_layouts(monkeypatch, layout, cfg_name, n_docs, voca
         np.testing.assert_array_equal(got.topk_score[q, :n], exp["topk_score"][q, :n])
 
 
+@pytest.mark.parametrize("seed", [1, 4, 5])
+def test_rank_directory_for_every_list(monkeypatch, seed):
+    """The marking pass finds secondary docs in a dense primary list through the rank directory; forcing a
+    directory for every list (PB_DIR_MIN_ROWS=1) runs that path on small random corpora."""
+    monkeypatch.setenv("PB_DIR_MIN_ROWS", "1")
+    rng = random.Random(8000 + seed)
+    n_fields = rng.choice([1, 2, 3])
+    docs = H.random_corpus(rng, rng.randint(30, 80), n_fields, multi_value=(seed % 2 == 0))
+    ix, o = both(docs, n_fields)
+    queries = [H.random_query(rng) for _ in range(40)] + ["a", "ab", "a b", "ab abc abcd a"]
+    compare_queries(ix, o, queries, [1.0] * n_fields, f"dir seed={seed}")
+    for k, _ in docs[::4]:
+        ix.remove_document(k)
+        o.remove_document(k)
+    compare_queries(ix, o, queries[:20], [1.0] * n_fields, f"dir seed={seed} removed")
+
+
 def test_long_fields_fall_back_to_wide_layout():
     """A field of 300 tokens / a tf of 300 does not fit a u16 (tf, fl) code: the device keeps u32 columns
     (and the BM25 table no longer covers every (tf, fl): the exact division path runs)."""
