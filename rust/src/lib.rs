@@ -65,6 +65,7 @@ struct PbQueryResults {
 }
 #[repr(C)] struct PbBuilder { _p: [u8; 0] }
 #[repr(C)] struct PbIndex { _p: [u8; 0] }
+#[repr(C)] struct PbImageFile { _p: [u8; 0] }
 
 extern "C" {
     fn pb_builder_create(num_fields: u32, out: *mut *mut PbBuilder) -> c_int;
@@ -75,6 +76,11 @@ extern "C" {
     fn pb_builder_flatten(b: *mut PbBuilder, out: *mut PbIndexImage) -> c_int;
     fn pb_index_create(image: *const PbIndexImage, device: c_int, out: *mut *mut PbIndex) -> c_int;
     fn pb_index_destroy(ix: *mut PbIndex);
+    // on-disk image (the reference has no serialisation): save what `flatten` produced, serve from a file
+    fn pb_image_save(image: *const PbIndexImage, path: *const c_char) -> c_int;
+    fn pb_image_load(path: *const c_char, out: *mut *mut PbImageFile) -> c_int;
+    fn pb_image_file_image(f: *const PbImageFile) -> *const PbIndexImage;
+    fn pb_image_file_free(f: *mut PbImageFile);
     fn pb_query_batch(ix: *mut PbIndex, q: *const PbQueryBatchDesc, out: *mut PbQueryResults) -> c_int;
     fn pb_query_full(ix: *mut PbIndex, q: *const PbQueryBatchDesc, cap: u64, out_query: *mut u32,
                      out_doc: *mut u32, out_score: *mut f64, n_total: *mut u64) -> c_int;
