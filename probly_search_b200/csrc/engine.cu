@@ -237,6 +237,7 @@ struct pb_batch {
   bool tab_full = false;
   // host staging
   std::vector<ull> h_recoff, h_binoff, h_gidx, h_gsegoff, h_gtileoff, h_bmoff;
+  bool h_full = false;           // the vectors above hold every entry (else only [0] and [Q])
   pb_batch_stats st{};
 
   ~pb_batch() {
@@ -517,6 +518,21 @@ constexpr uint64_t REC_CAP_MAX = 1ull << 31;
 constexpr uint64_t BIN_CAP = 96ull << 20;               // doc-range bins per round (12 B each)
 constexpr uint64_t BITMAP_POOL_BYTES = 6ull << 30;    // per-query doc bitmaps of one round
 
+int fetch_prefix_arrays(pb_batch* b) {
+  if (b->h_full) return PB_OK;
+  const uint64_t Q = b->Q;
+  cudaStream_t st = b->stream;
+  CU(cudaMemcpyAsync(b->h_bmoff.data(), b->q_bmoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(b->h_recoff.data(), b->q_recoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(b->h_binoff.data(), b->q_binoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(b->h_gidx.data(), b->q_gidx.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(b->h_gsegoff.data(), b->q_gsegoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(b->h_gtileoff.data(), b->q_gtileoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  b->h_full = true;
+  return PB_OK;
+}
+
 int batch_run(pb_batch* b) {
   pb_index* ix = b->ix;
   if (!b->loaded) { pb::set_error("pb_batch_run: batch not loaded"); return PB_ERR_INVALID; }
@@ -585,10 +601,11 @@ int batch_run(pb_batch* b) {
                                                    b->q_prim.p, b->stats.p + ST_COUNT);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(b->q_bmwords.p, 0, (Q + 2) * sizeof(ull), st));
+    CU(cudaMemsetAsync(b->xcount.p + 2, 0, 2 * sizeof(ull), st));      // per-query maxima: records, mask words
     gprimary_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q, doc_bits, b->q_isg.p, b->q_grows.p, b->q_prim.p,
                                                                      b->seg_g.p, b->q_recbound.p, b->q_nbins.p, b->q_scheme.p,
                                                                      b->q_shift.p, b->query_term_off.p, b->qt_goff.p,
-                                                                     b->q_gsegoff.p, b->q_bmwords.p, bitmap_words);
+                                                                     b->q_gsegoff.p, b->q_bmwords.p, bitmap_words, b->xcount.p + 2);
     CU(cudaGetLastError());
     RC(scan_ull(b, b->g_tiles.p, b->g_tile_off.p, n_gsegs + 1));
     RC(scan_ull(b, b->q_recbound.p, b->q_recoff.p, Q + 1));
@@ -598,24 +615,31 @@ int batch_run(pb_batch* b) {
     gather_tileoff_kernel<<<(unsigned)((Q + 1 + 255) / 256), 256, 0, st>>>(Q + 1, b->q_gsegoff.p, b->g_tile_off.p, b->q_gtileoff.p);
     CU(cudaGetLastError());
     launches += 8;
-    b->h_binoff.resize(Q + 1); b->h_bmoff.resize(Q + 1);
-    CU(cudaMemcpyAsync(b->h_bmoff.data(), b->q_bmoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    b->h_recoff.resize(Q + 1); b->h_gidx.resize(Q + 1); b->h_gsegoff.resize(Q + 1); b->h_gtileoff.resize(Q + 1);
-    CU(cudaMemcpyAsync(b->h_recoff.data(), b->q_recoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(b->h_binoff.data(), b->q_binoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(b->h_gidx.data(), b->q_gidx.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(b->h_gsegoff.data(), b->q_gsegoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(b->h_gtileoff.data(), b->q_gtileoff.p, (Q + 1) * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    // rounds: contiguous query ranges whose record bound and bitmap slots fit the workspace
-    pool_words = BITMAP_POOL_BYTES / 4;
-    rec_cap = REC_CAP_DEFAULT;
-    for (uint64_t q = 0; q < Q; ++q) {
-      rec_cap = std::max<uint64_t>(rec_cap, b->h_recoff[q + 1] - b->h_recoff[q]);
-      pool_words = std::max<uint64_t>(pool_words, b->h_bmoff[q + 1] - b->h_bmoff[q]);     // one query always fits
+    // Round planning needs the per-query prefix arrays on the host only when the side path does not
+    // fit ONE round; the totals and the per-query maxima (8 scalars) decide that.
+    for (auto* v : {&b->h_binoff, &b->h_bmoff, &b->h_recoff, &b->h_gidx, &b->h_gsegoff, &b->h_gtileoff}) {
+      if (v->size() != Q + 1) v->assign(Q + 1, 0);      // entry [0] of an exclusive prefix is always 0
     }
+    ull h_max[2] = {0, 0};
+    CU(cudaMemcpyAsync(&b->h_bmoff[Q], b->q_bmoff.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&b->h_recoff[Q], b->q_recoff.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&b->h_binoff[Q], b->q_binoff.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&b->h_gidx[Q], b->q_gidx.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&b->h_gsegoff[Q], b->q_gsegoff.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&b->h_gtileoff[Q], b->q_gtileoff.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_max, b->xcount.p + 2, 2 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    pool_words = std::max<uint64_t>(BITMAP_POOL_BYTES / 4, h_max[1]);       // one query always fits
+    rec_cap = std::max<uint64_t>(REC_CAP_DEFAULT, h_max[0]);
     if (rec_cap > REC_CAP_MAX) { pb::set_error("a single query needs %llu side-path records (> %llu)", (ull)rec_cap, (ull)REC_CAP_MAX); return PB_ERR_UNSUPPORTED; }
+    b->h_full = false;
+    if (b->h_recoff[Q] > rec_cap || b->h_bmoff[Q] > pool_words || b->h_binoff[Q] > BIN_CAP) RC(fetch_prefix_arrays(b));
     uint64_t qa = 0;
+    if (!b->h_full) {               // everything fits one round: only entries [0] and [Q] of the arrays are needed
+      Round r{0, Q, 0, b->h_gsegoff[Q], 0, b->h_gtileoff[Q], b->h_gidx[Q], b->h_recoff[Q], b->h_bmoff[Q]};
+      if (r.sb > r.sa) rounds.push_back(r);
+      qa = Q;
+    }
     while (qa < Q) {
       // largest qb with recoff[qb]-recoff[qa] <= rec_cap and bmoff[qb]-bmoff[qa] <= pool_words
       uint64_t qb1 = std::upper_bound(b->h_recoff.begin() + qa, b->h_recoff.end(), b->h_recoff[qa] + rec_cap) - b->h_recoff.begin() - 1;
@@ -748,6 +772,7 @@ int batch_run(pb_batch* b) {
       if (need > rec_cap) {
         RC(clear_marks(false));                 // nothing was scored yet
         if (r.qb - r.qa > 1) {
+          RC(fetch_prefix_arrays(b));           // splitting needs the per-query prefixes
           uint64_t mid = r.qa + (r.qb - r.qa) / 2;
           work.push_back(make_round(mid, r.qb));
           work.push_back(make_round(r.qa, mid));
@@ -789,18 +814,6 @@ int batch_run(pb_batch* b) {
         CU(cudaMemcpyAsync(&h_over, b->counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaMemsetAsync(b->counters.p + 3, 0, sizeof(uint32_t), st));
-        if (std::getenv("PB_DEBUG")) {
-          std::vector<uint32_t> hc(n_bins);
-          CU(cudaMemcpy(hc.data(), b->bin_cursor.p, n_bins * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-          uint64_t hist[8] = {0}; uint64_t big_bins = 0; uint32_t mx = 0; uint64_t mxi = 0;
-          for (uint64_t i = 0; i < n_bins; ++i) { uint32_t c = hc[i]; int k = c == 0 ? 0 : c <= 4 ? 1 : c <= 8 ? 2 : c <= 16 ? 3 : c <= 32 ? 4 : c <= 128 ? 5 : c <= 1024 ? 6 : 7; hist[k] += c; if (c > 32) ++big_bins; if (c > mx) { mx = c; mxi = i; } }
-          uint64_t qq = std::upper_bound(b->h_binoff.begin(), b->h_binoff.end(), b->h_binoff[r.qa] + mxi) - b->h_binoff.begin() - 1;
-          std::vector<uint8_t> hs(Q); std::vector<uint8_t> hsc(Q);
-          CU(cudaMemcpy(hs.data(), b->q_shift.p, Q, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(hsc.data(), b->q_scheme.p, Q, cudaMemcpyDeviceToHost));
-          fprintf(stderr, "[pb] records by bin size 0:%llu <=4:%llu <=8:%llu <=16:%llu <=32:%llu <=128:%llu <=1024:%llu more:%llu | bins>32: %llu | max bin %u (query %llu, bins of query %llu, shift %u scheme %u recbound %llu)\n",
-                  (ull)hist[0], (ull)hist[1], (ull)hist[2], (ull)hist[3], (ull)hist[4], (ull)hist[5], (ull)hist[6], (ull)hist[7], (ull)big_bins, mx, (ull)qq,
-                  (ull)(b->h_binoff[qq + 1] - b->h_binoff[qq]), hs[qq], hsc[qq], (ull)(b->h_recoff[qq + 1] - b->h_recoff[qq]));
-        }
         if (std::getenv("PB_DEBUG"))
           fprintf(stderr, "[pb] round q[%llu,%llu) segs %llu tiles %llu bins %llu need %llu overflow %u exact_tiles %llu words %llu\n",
                   (ull)r.qa, (ull)r.qb, (ull)nseg, (ull)tiles, (ull)n_bins, (ull)need, h_over, (ull)exact_tiles, (ull)r.words);

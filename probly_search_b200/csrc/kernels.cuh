@@ -204,6 +204,9 @@ struct ScoreParams {
 #ifndef PB_LDPOLICY
 #define PB_LDPOLICY 0
 #endif
+#ifndef PB_L2_AHEAD
+#define PB_L2_AHEAD 6
+#endif
 __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
   uint4 r;
 #if PB_LDPOLICY == 0
@@ -647,7 +650,7 @@ __global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const uns
                                 const uint64_t* __restrict__ query_term_off,
                                 const unsigned long long* __restrict__ qt_goff,
                                 unsigned long long* __restrict__ q_gsegoff, unsigned long long* __restrict__ q_bmwords,
-                                uint32_t bitmap_words) {
+                                uint32_t bitmap_words, unsigned long long* __restrict__ qmax) {
   uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (q > n_queries) return;
   q_gsegoff[q] = qt_goff[query_term_off[q]];   // qt_goff has n_qterms + 1 entries
@@ -682,6 +685,7 @@ __global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const uns
   }
   q_recbound[q] = bound;
   q_bmwords[q] = bmw;
+  if (bound) { atomicMax(&qmax[0], bound); atomicMax(&qmax[1], bmw); }     // largest single query (host: capacities)
   q_nbins[q] = nbins;
   q_scheme[q] = scheme;
   q_shift[q] = shift;
@@ -973,7 +977,7 @@ struct SegCtx {
 // One tile = 128 aligned rows; lane l owns rows 4l..4l+3 (one 128-bit load per u32 column, one
 // 32-bit load per u8 column).
 //   EDGE : the tile is shared with neighbouring segments -> per-row range mask
-//   FAST : no removed docs, no full-result capture, complete BM25 table -> no per-row checks
+//   FAST : no full-result capture, complete BM25 table -> no per-row table range checks
 template <int F, bool NARROW> struct TileGeom {
   static constexpr uint32_t WORDS = NARROW ? (TILE_ROWS + F * TILE_ROWS / 2) : (1 + 2 * F) * TILE_ROWS;   // u32 words per tile
 };
@@ -1037,7 +1041,7 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
       valid |= (r >= lo && r < hi) ? (1u << j) : 0u;
     }
   }
-  if (!FAST && P.ix.has_removed) {      // removed-but-not-vacuumed docs are skipped (query.rs:65)
+  if (P.ix.has_removed) {               // removed-but-not-vacuumed docs are skipped (query.rs:65)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (((valid >> j) & 1u) && ((__ldg(&P.ix.removed[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) valid &= ~(1u << j);
@@ -1160,6 +1164,12 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
     for (uint32_t i = 0; i < n_tiles; ++i) {
       TileRegs<F, NARROW> nxt;
       load_tile<F, GMODE, NARROW>(C, base + TileGeom<F, NARROW>::WORDS, nullptr, lane, nxt);
+#if PB_L2_AHEAD
+      // an image larger than L2 (cfg 3/4: 2.1 GB) streams from HBM: one tile of register look-ahead does
+      // not cover DRAM latency, so the lines of the tile PB_L2_AHEAD tiles further on are pulled into L2
+      if (i + PB_L2_AHEAD < n_tiles && lane < (int)(TileGeom<F, NARROW>::WORDS / 32))
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + PB_L2_AHEAD * TileGeom<F, NARROW>::WORDS + lane * 32));
+#endif
       const uint32_t mw2 = ld_mask(maskp + 8);       // mask of tile i + 2
       // a primary-list tile whose row-mask bits are all clear diverts nothing: score it exactly like a
       // single-list tile (the common case: ~93 % of the tiles of the cfg 1 batch)
@@ -1215,7 +1225,7 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 1) score_kernel(const __gri
   bool acc_owned = false;
   uint32_t st_div = 0;
   // launch-wide: may the interior tiles take the check-free path?
-  const bool fast = !P.ix.has_removed && P.out.full_q == nullptr && (SCORER != 0 || P.tab_full);
+  const bool fast = P.out.full_q == nullptr && (SCORER != 0 || P.tab_full);
 
   while (t < span1) {
     const Seg sg = P.segs[s];
