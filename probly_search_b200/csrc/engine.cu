@@ -573,6 +573,9 @@ int batch_run(pb_batch* b) {
                                                                  b->qt_q.p, b->q_isg.p, b->q_grows.p, b->stats.p);
   CU(cudaGetLastError());
   ++launches;
+  // the exclusive scans below run over n + 1 entries: give the extra input entry a defined value
+  CU(cudaMemsetAsync(b->s_tiles.p + Q, 0, sizeof(ull), st));
+  CU(cudaMemsetAsync(b->qt_gcount.p + NT, 0, sizeof(ull), st));
   RC(scan_ull(b, b->s_tiles.p, b->s_tile_off.p, Q + 1));
   RC(scan_ull(b, b->qt_gcount.p, b->qt_goff.p, NT + 1));
   launches += 2;
@@ -607,6 +610,10 @@ int batch_run(pb_batch* b) {
                                                                      b->q_shift.p, b->query_term_off.p, b->qt_goff.p,
                                                                      b->q_gsegoff.p, b->q_bmwords.p, bitmap_words, b->xcount.p + 2);
     CU(cudaGetLastError());
+    CU(cudaMemsetAsync(b->g_tiles.p + n_gsegs, 0, sizeof(ull), st));
+    CU(cudaMemsetAsync(b->q_recbound.p + Q, 0, sizeof(ull), st));
+    CU(cudaMemsetAsync(b->q_nbins.p + Q, 0, sizeof(ull), st));
+    CU(cudaMemsetAsync(b->q_isg.p + Q, 0, sizeof(ull), st));
     RC(scan_ull(b, b->g_tiles.p, b->g_tile_off.p, n_gsegs + 1));
     RC(scan_ull(b, b->q_recbound.p, b->q_recoff.p, Q + 1));
     RC(scan_ull(b, b->q_nbins.p, b->q_binoff.p, Q + 1));
