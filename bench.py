@@ -184,10 +184,6 @@ def main():
         fq_all = wl.queries(min(n_queries, 20_000))
         o, run, n = cpu_arm(cfg, wl, n_docs, fq_all, scorer_id, threads, target_s=12.0)
         fq = fq_all.slice(0, n)
-        # de-duplicated rows of the sample (the metric's unit): count them from the oracle's own structures
-        rows = 0
-        for q in range(fq.n_queries):
-            pass
         for _ in range(warmup):
             run(fq)
         secs, ptr = 0.0, 0

@@ -4,15 +4,19 @@
 //   descend_kernel     find_inverted_index_node (index.rs:300-337) over the CSR trie; because
 //                      nodes/terms are numbered in DFS pre-order the whole of expand_term
 //                      (query.rs:109-147) collapses to the term range [lo, hi) of the node.
-//   plan_*             per query: how many live expanded lists, which class (single list ->
-//                      streamed directly; several lists -> primary list streamed + the rest
-//                      through the sort/fold side path), segment descriptors.
+//   plan_* / g*_kernel per query: how many live expanded lists, which class (single list ->
+//                      streamed directly; several lists -> side path: primary / exact scheme),
+//                      segment descriptors, doc-range bins, row-mask / bitmap words.
 //   live_df_kernel     count_documents (index.rs:282-297) for every term at once.
+//   dir_*_kernel       rank directories of the dense posting lists (built once per index).
 //   score_kernel       THE hot loop (query.rs:61-89): posting rows -> removed mask -> BM25 /
 //                      zero-to-one -> fused count / digest / top-k, or diversion to the side path.
-//   mark_kernel        marks docs that occur in a non-primary list of a multi-list query.
-//   fold_kernel        max_score_merger (query.rs:150-164) and ZeroToOne::finalize
-//                      (zero_to_one.rs:84-126) on docs that received several events.
+//   mark_kernel        side path, pass 1: which rows of a multi-list query belong to docs hit by
+//                      several (query term, expansion) events (row masks / doc bitmaps), and how
+//                      many records every doc-range bin will receive.
+//   binfold_kernel     side path, pass 3: max_score_merger (query.rs:150-164) and
+//   (fold_kernel)      ZeroToOne::finalize (zero_to_one.rs:84-126) on the diverted events, per doc,
+//                      in (query term, expansion) order; fold_kernel is the sorted fallback.
 //   finalize_kernel    merges per-warp partial top-k lists (query.rs:97-105: result + sort).
 //
 // f64 arithmetic is done with __d*_rn intrinsics in the reference's operation order, so no FMA
@@ -54,7 +58,7 @@ struct __align__(16) Seg {
   uint16_t qti;        // query_term_index (query.rs:34)
   uint8_t mode;
   uint8_t pad;
-  uint32_t slot;       // bitmap slot of the query inside its side-path round
+  uint32_t slot;       // rank of the query among the class-G queries of its side-path round (sorted-fallback key)
 };
 static_assert(sizeof(Seg) == 32, "Seg layout");
 
@@ -691,7 +695,7 @@ __global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const uns
   q_shift[q] = shift;
 }
 
-// Assign bitmap slots for one round: slot = rank of the query among the round's class-G queries.
+// Per round: slot = rank of the query among the round's class-G queries (key of the sorted fallback).
 // Also writes the tile count of every list the MARKING pass walks (all but the primary lists): its
 // prefix sum is the marking pass's own tile space, so that its warps share that work evenly.
 __global__ void gslot_kernel(Seg* __restrict__ seg_g, uint64_t seg_begin, uint64_t seg_end,
