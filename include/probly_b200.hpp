@@ -96,6 +96,14 @@ class Index {
   }
   void vacuum() { check(pb_builder_vacuum(b_)); dirty_ = true; }
 
+  // Not in the reference (it has no serialisation): writes the flattened image a serving process can
+  // load with pb_image_load + pb_index_create, without building this mutable index.
+  void save_image(const std::string& path) {
+    pb_index_image im;
+    check(pb_builder_flatten(b_, &im));
+    check(pb_image_save(&im, path.c_str()));
+  }
+
   template <class S>
   std::vector<QueryResult<T>> query(std::string_view query, S& score_calculator, Tokenizer tokenizer,
                                     const std::vector<double>& fields_boost) {

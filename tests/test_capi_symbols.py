@@ -67,3 +67,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower() or f in ("workload.py", "workload.cpp", "index.py"), f
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_device():
+    L = capi.lib()
+    assert L.pb_index_device_layout(None, None) == capi.PB_ERR_INVALID
+    g = C.c_double(0.0)
+    assert L.pb_device_read_bandwidth(0, 16, 1, C.byref(g)) == capi.PB_ERR_INVALID          # buffer too small
+    if L.pb_device_count() == 0:
+        assert L.pb_device_read_bandwidth(0, 1 << 20, 1, C.byref(g)) == capi.PB_ERR_NO_DEVICE
+    assert L.pb_image_save(None, b"/tmp/x") == capi.PB_ERR_INVALID
+    h = C.c_void_p()
+    assert L.pb_image_load(None, C.byref(h)) == capi.PB_ERR_INVALID
+    assert L.pb_image_file_image(None) is None
+    L.pb_image_file_free(None)                                                               # no-op, must not crash
