@@ -18,6 +18,10 @@
 //  (SURVEY.md §8c): src/score/default/bm25.rs:104-136, src/query.rs:181-387,
 //  src/score/default/zero_to_one.rs:138-404, tests/integrations_tests.rs:27-149,
 //  tests/document_frequency.rs:5-32, src/index.rs:492-784.
+//  NOT pinned by any reference test: BM25 with boosts != 1, the
+//  pre-vacuum removed mask under BM25, the merger across several terms AND
+//  expansions, non-ASCII byte lengths, multi-valued fields.  There this
+//  restatement of the cited lines is the only authority.
 //  The real crate cannot be compiled here (no rustc/cargo, un-vendored
 //  hashbrown 0.14 / typed-generational-arena 0.2), so there is no oracle/_ref.
 //

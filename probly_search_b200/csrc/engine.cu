@@ -1103,17 +1103,19 @@ int pb_device_read_bandwidth(int device, uint64_t bytes, uint32_t iters, double*
   CU(sink.ensure(1));
   CU(cudaMemset(buf.p, 1, n * sizeof(uint4)));
   CU(cudaMemset(sink.p, 0, sizeof(ull)));
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  struct Events {      // destroyed on every return path
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  } ev;
+  CU(cudaEventCreate(&ev.e0)); CU(cudaEventCreate(&ev.e1));
   const int grid = g_sm_count(device) * 8;
   read_bw_kernel<<<grid, 256>>>(buf.p, n, 1, sink.p);
-  CU(cudaEventRecord(e0));
+  CU(cudaEventRecord(ev.e0));
   read_bw_kernel<<<grid, 256>>>(buf.p, n, iters, sink.p);
-  CU(cudaEventRecord(e1));
-  CU(cudaEventSynchronize(e1));
+  CU(cudaEventRecord(ev.e1));
+  CU(cudaEventSynchronize(ev.e1));
   float ms = 0;
-  CU(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
   CU(cudaGetLastError());
   *gb_per_s = (double)n * sizeof(uint4) * iters / (ms * 1e-3) / 1e9;
   return PB_OK;
