@@ -113,6 +113,7 @@ struct pb_index {
   DBuf<uint32_t> term_byte_len, post_blocks, removed, live_prefix, term_live_rows;
   DBuf<uint64_t> term_df_live, liverows_prefix;
   DBuf<double> term_idf, eb;
+  DBuf<double> rcp;             // RN(1 / d), d = 0..1024 (PB_Z2O_RCP experiment, kernels.cuh)
   DBuf<uint2> dir;              // rank directories of the dense posting lists (IndexView::dir)
   DBuf<uint32_t> term_dir;
   uint32_t dir_words = 0, n_dense = 0;
@@ -135,6 +136,7 @@ struct pb_index {
     v.term_df_live = term_df_live.p; v.term_live_rows = term_live_rows.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
     v.term_idf = term_idf.p; v.eb = eb.p;
     v.dir = dir.p; v.term_dir = term_dir.p; v.dir_words = dir_words;
+    v.rcp = rcp.p; v.rcp_ok = max_term_bytes <= 255u ? 1u : 0u;
     v.n_terms = (uint32_t)n_terms; v.n_docs = (uint32_t)n_docs; v.num_fields = F;
     v.has_removed = n_removed ? 1u : 0u;
     return v;
@@ -1032,6 +1034,11 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
     ix->h_node_char.assign(im->node_char, im->node_char + im->n_nodes);
     ix->h_term_node.assign(im->term_node, im->term_node + im->n_terms);
     ix->h_term_row_begin.assign(im->term_row_begin, im->term_row_begin + im->n_terms + 1);
+    {
+      std::vector<double> rc(1025, 0.0);
+      for (int d = 1; d <= 1024; ++d) rc[d] = 1.0 / (double)d;     // correctly rounded by the host division
+      CU(upload(ix->rcp, rc.data(), rc.size()));
+    }
     // expansion boost by byte-length delta, bm25.rs:45-53 (libm log on the host)
     std::vector<double> eb(im->max_term_bytes + 2, 1.0);
     for (size_t d = 1; d < eb.size(); ++d) eb[d] = std::log(1.0 + (1.0 / (1.0 + (double)d)));   // (1 + explen) - qlen = 1 + d exactly

@@ -94,6 +94,8 @@ struct IndexView {
   const uint2* dir;               // [n_dense][dir_words]
   const uint32_t* term_dir;       // [n_terms] 1 + index of the term's directory, 0 = none
   uint32_t dir_words;
+  const double* rcp;              // [1025] RN(1 / d), d = 1..1024 (PB_Z2O_RCP experiment; host-computed)
+  uint32_t rcp_ok;                // every term is at most 255 bytes long: the proven domain of that experiment
   uint32_t n_terms;
   uint32_t n_docs;
   uint32_t num_fields;
@@ -272,11 +274,31 @@ __device__ __forceinline__ double z2o_term_score(uint32_t explen, uint32_t qlen)
   double e = (double)explen, q = (double)qlen;
   return __dsub_rn(1.0, __ddiv_rn(fabs(__dsub_rn(e, q)), e));
 }
+// PB_Z2O_RCP = 1 (EXPERIMENT, default off, not yet run on a GPU): both divisions of the ZeroToOne entry
+// below become  y = RN(1/d) from a 1025-entry table,  q = RN(x y),  r = fma(-q, d, x),  q' = fma(r, y, q).
+// scripts/prove_z2o_rcp.c compares q' with the real quotient, bit for bit, for EVERY (term score, tf, m)
+// the guard lets through (term byte lengths <= 255, tf <= 64, m <= 1024): 2.1e9 cases, 0 mismatches.
+#ifndef PB_Z2O_RCP
+#define PB_Z2O_RCP 0
+#endif
+__device__ __forceinline__ double div_small_int_rcp(double x, uint32_t d, const double* __restrict__ rcp) {
+  const double y = __ldg(&rcp[d]);
+  const double q = __dmul_rn(x, y);
+  const double r = __fma_rn(-q, (double)d, x);
+  return __fma_rn(r, y, q);
+}
 // zero_to_one.rs:117-120 — min(s/tf, 1) * tf / max(field_length, query_terms_len)
-__device__ __forceinline__ double z2o_entry(double s, uint32_t tf, uint32_t fl, uint32_t qtl) {
+__device__ __forceinline__ double z2o_entry(const IndexView& ix, double s, uint32_t tf, uint32_t fl, uint32_t qtl) {
+  const uint32_t m = max(fl, qtl);
+#if PB_Z2O_RCP
+  if (ix.rcp_ok && tf <= 64u && m <= 1024u) {
+    const double v = __dmul_rn(fmin(div_small_int_rcp(s, tf, ix.rcp), 1.0), (double)tf);
+    return div_small_int_rcp(v, m, ix.rcp);
+  }
+#endif
   double tfd = (double)tf;
   double v = __dmul_rn(fmin(__ddiv_rn(s, tfd), 1.0), tfd);
-  return __ddiv_rn(v, (double)max(fl, qtl));
+  return __ddiv_rn(v, (double)m);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -930,7 +952,7 @@ __device__ __forceinline__ void z2o_rows(const ScoreParams& P, const TileRegs<F,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t tf = R.tf(P.ix, f, j), fl = R.fl(P.ix, f, j);
-      if (tf > 0) sc[j] = fmax(z2o_entry(zs, tf, fl, qtl), sc[j]);
+      if (tf > 0) sc[j] = fmax(z2o_entry(P.ix, zs, tf, fl, qtl), sc[j]);
     }
   }
 }
@@ -1397,7 +1419,7 @@ __device__ __noinline__ bool fold_group_slow(const FoldParams& FP, uint32_t i, u
         }
         if (consumed || used >= btf) continue;
         acc_lo |= 1ull << bj;
-        accx = __dadd_rn(accx, z2o_entry(bs, btf, bfl, qtl));
+        accx = __dadd_rn(accx, z2o_entry(P.ix, bs, btf, bfl, qtl));
       }
       result = fmax(accx, result);
     }
@@ -1494,7 +1516,7 @@ __device__ __forceinline__ void fold_window(const ScoreParams& P, WarpAcc& acc, 
         const uint32_t used = __popc(__ballot_sync(0xffffffffu, accepted && e_term == c_term) & gmask);
         const bool ok = m < size && c_tf > 0 && conflict == 0u && used < c_tf;
         double contrib = 0.0;
-        if (ok && pos == m) { accepted = true; contrib = z2o_entry(ev_score, tfv[x], flv[x], qtl); }
+        if (ok && pos == m) { accepted = true; contrib = z2o_entry(P.ix, ev_score, tfv[x], flv[x], qtl); }
         contrib = shfl_f64(contrib, c);
         if (ok) accx = __dadd_rn(accx, contrib);
       }
