@@ -1714,11 +1714,6 @@ __global__ void __launch_bounds__(CTA_THREADS) binfold_kernel(const __grid_const
     unsigned long long key = ~0ull;
     if (in) {
       r = P.rec[t_off + (lane - (t_incl - t_cnt))];
-#ifdef PB_DEBUG_PHANTOM
-      if (r.x == 0 && r.y == 0 && r.z == 0 && r.w == 0)
-        printf("phantom: bin %u (+%d) cnt %u off %u cap_end %u idx %u lane %d total %u nb_take %d b %u b1 %u\n", b + t, t, t_cnt, t_off,
-               P.bin_off[b + t + 1], lane - (t_incl - t_cnt), lane, total, nb_take, b, b1);
-#endif
       sg = P.segs[r.y];
       const unsigned long long segrel = (unsigned long long)r.y - P.q_gsegoff[sg.q];
       if (segrel >> 27) atomicOr(P.out.error_flag, 8u);       // > 2^27 posting lists in one query
