@@ -20,7 +20,8 @@
 #include <cub/cub.cuh>
 
 #include "common.hpp"
-#include "kernels.cuh"
+#include "field_ops.hpp"
+#include "plan_kernels.cuh"
 
 using namespace pbk;
 typedef unsigned long long ull;
@@ -163,13 +164,7 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
   if (NT) {
     IndexView v = ix->view();
     int grid = ix->sm_count * 8;
-    switch (ix->F) {
-      case 1: live_df_kernel<1><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
-      case 2: live_df_kernel<2><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
-      case 3: live_df_kernel<3><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
-      default: live_df_kernel<4><<<grid, 256>>>(v, (ull*)ix->term_df_live.p, ix->term_live_rows.p); break;
-    }
-    CU(cudaGetLastError());
+    CU(field_ops(ix->F)->live_df_launch(&v, (ull*)ix->term_df_live.p, ix->term_live_rows.p, grid, 0));
   }
   ix->h_df_live.assign(NT + 1, 0);
   CU(cudaMemcpy(ix->h_df_live.data(), ix->term_df_live.p, NT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -396,37 +391,6 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   return PB_OK;
 }
 
-template <int F, int SC, bool G, bool N>
-int launch_score_t(pb_batch* b, const ScoreParams& P, int grid, int threads, size_t smem) {
-  score_kernel<F, SC, G, N><<<grid, threads, smem, b->stream>>>(P);
-  CU(cudaGetLastError());
-  return PB_OK;
-}
-template <int F, int SC, bool G, bool N>
-int occupancy_score_t(int* per_sm, int threads, size_t smem) {
-  CU(cudaFuncSetAttribute(score_kernel<F, SC, G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G, N>, threads, smem));
-  return PB_OK;
-}
-
-template <int V> using IC = std::integral_constant<int, V>;
-
-// run fn(IC<F>, IC<SCORER>) for the runtime (field count, scorer) pair
-template <class Fn>
-int dispatch_fs(uint32_t F, uint32_t scorer, Fn&& fn) {
-  switch (F * 2 + scorer) {
-    case 2: return fn(IC<1>{}, IC<0>{});
-    case 3: return fn(IC<1>{}, IC<1>{});
-    case 4: return fn(IC<2>{}, IC<0>{});
-    case 5: return fn(IC<2>{}, IC<1>{});
-    case 6: return fn(IC<3>{}, IC<0>{});
-    case 7: return fn(IC<3>{}, IC<1>{});
-    case 8: return fn(IC<4>{}, IC<0>{});
-    case 9: return fn(IC<4>{}, IC<1>{});
-    default: pb::set_error("unsupported field count / scorer"); return PB_ERR_UNSUPPORTED;
-  }
-}
-
 // Shared-memory plan of the scoring kernel: how many copies of the BM25 table (16 = conflict-free
 // LDS.64, see ScoreParams::tab_rep_shift) fit, and the CTA shape that keeps ~24 warps per SM resident.
 struct ScorePlan { uint32_t rep_shift; int threads; size_t smem; };
@@ -450,68 +414,42 @@ ScorePlan score_plan(const pb_batch* b, uint32_t tab_total) {
 }
 
 int launch_score(pb_batch* b, ScoreParams& P, bool gmode, uint64_t tiles) {
-  return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
-    constexpr int F = decltype(f)::value, SC = decltype(sc)::value;
-    const ScorePlan sp = score_plan(b, P.tab_total);
-    P.tab_rep_shift = sp.rep_shift;
-    P.tab_stride = 8u << sp.rep_shift;
-    for (int x = 0; x < 4; ++x) P.tab_boff[x] = P.tab_off[x] * P.tab_stride;
-    int per_sm = 1;
-    const bool nw = b->ix->narrow;
-    if (gmode && nw) RC((occupancy_score_t<F, SC, true, true>(&per_sm, sp.threads, sp.smem)));
-    else if (gmode) RC((occupancy_score_t<F, SC, true, false>(&per_sm, sp.threads, sp.smem)));
-    else if (nw) RC((occupancy_score_t<F, SC, false, true>(&per_sm, sp.threads, sp.smem)));
-    else RC((occupancy_score_t<F, SC, false, false>(&per_sm, sp.threads, sp.smem)));
-    if (per_sm < 1) { pb::set_error("scoring kernel does not fit an SM (%d threads, %zu B shared)", sp.threads, sp.smem); return PB_ERR_CUDA; }
-    // one warp = one contiguous span of tiles; never more warps than there is work for
-    const uint64_t warps_per_cta = (uint64_t)sp.threads / 32;
-    uint64_t max_grid = (uint64_t)b->ix->sm_count * per_sm;
-    uint64_t want = (tiles + warps_per_cta * 2 - 1) / (warps_per_cta * 2);
-    int grid = (int)std::max<uint64_t>(1, std::min(max_grid, want));
-    if (gmode && nw) return launch_score_t<F, SC, true, true>(b, P, grid, sp.threads, sp.smem);
-    if (gmode) return launch_score_t<F, SC, true, false>(b, P, grid, sp.threads, sp.smem);
-    if (nw) return launch_score_t<F, SC, false, true>(b, P, grid, sp.threads, sp.smem);
-    return launch_score_t<F, SC, false, false>(b, P, grid, sp.threads, sp.smem);
-  });
+  const FieldOps* ops = field_ops(b->ix->F);
+  const int sc = (int)b->scorer;
+  const bool nw = b->ix->narrow;
+  const ScorePlan sp = score_plan(b, P.tab_total);
+  P.tab_rep_shift = sp.rep_shift;
+  P.tab_stride = 8u << sp.rep_shift;
+  for (int x = 0; x < 4; ++x) P.tab_boff[x] = P.tab_off[x] * P.tab_stride;
+  int per_sm = 1;
+  CU(ops->score_occupancy(sc, gmode, nw, &per_sm, sp.threads, sp.smem));
+  if (per_sm < 1) { pb::set_error("scoring kernel does not fit an SM (%d threads, %zu B shared)", sp.threads, sp.smem); return PB_ERR_CUDA; }
+  // one warp = one contiguous span of tiles; never more warps than there is work for
+  const uint64_t warps_per_cta = (uint64_t)sp.threads / 32;
+  uint64_t max_grid = (uint64_t)b->ix->sm_count * per_sm;
+  uint64_t want = (tiles + warps_per_cta * 2 - 1) / (warps_per_cta * 2);
+  int grid = (int)std::max<uint64_t>(1, std::min(max_grid, want));
+  CU(ops->score_launch(sc, gmode, nw, &P, grid, sp.threads, sp.smem, b->stream));
+  return PB_OK;
 }
 
 int launch_mark(pb_batch* b, const ScoreParams& P, int grid, int clear) {
-  switch (b->ix->F) {
-    case 1: mark_kernel<1><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
-    case 2: mark_kernel<2><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
-    case 3: mark_kernel<3><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
-    default: mark_kernel<4><<<grid, CTA_THREADS, 0, b->stream>>>(P, clear); break;
-  }
-  CU(cudaGetLastError());
+  CU(field_ops(b->ix->F)->mark_launch(&P, clear, grid, b->stream));
   return PB_OK;
 }
 
-template <int F, int SC>
-int launch_fold_t(pb_batch* b, const FoldParams& FP, int grid) {
-  fold_kernel<F, SC><<<grid, CTA_THREADS, 0, b->stream>>>(FP);
-  CU(cudaGetLastError());
-  return PB_OK;
-}
 int launch_fold(pb_batch* b, const FoldParams& FP) {
   uint64_t want = ((uint64_t)FP.n + CTA_THREADS - 1) / CTA_THREADS;
   int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)b->ix->sm_count * 4, want));
-  return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
-    return launch_fold_t<decltype(f)::value, decltype(sc)::value>(b, FP, grid);
-  });
-}
-
-template <int F, int SC>
-int launch_binfold_t(pb_batch* b, const ScoreParams& P, int grid) {
-  binfold_kernel<F, SC><<<grid, CTA_THREADS, 0, b->stream>>>(P);
-  CU(cudaGetLastError());
+  CU(field_ops(b->ix->F)->fold_launch((int)b->scorer, &FP, grid, b->stream));
   return PB_OK;
 }
+
 int launch_binfold(pb_batch* b, const ScoreParams& P, uint64_t n_bins) {
   uint64_t want = (n_bins + WARPS_PER_CTA * 4 - 1) / (WARPS_PER_CTA * 4);
   int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)b->ix->sm_count * 6, want));
-  return dispatch_fs(b->ix->F, b->scorer, [&](auto f, auto sc) -> int {
-    return launch_binfold_t<decltype(f)::value, decltype(sc)::value>(b, P, grid);
-  });
+  CU(field_ops(b->ix->F)->binfold_launch((int)b->scorer, &P, grid, b->stream));
+  return PB_OK;
 }
 
 // Side-path capacity knobs (bytes of HBM the workspace may take).

@@ -439,44 +439,6 @@ struct WarpAcc {
   }
 };
 
-// ------------------------------------------------------------------------------------------
-// Trie descent + prefix expansion
-// ------------------------------------------------------------------------------------------
-// One thread per query term.  find_inverted_index_node (index.rs:300-318) with a binary search
-// over the node's char-sorted edges instead of the sibling-list scan (index.rs:321-337).
-// Output: the DFS term range [lo, hi) = expand_term's result (query.rs:109-147), already in the
-// reference's expansion order; lo == hi when nothing matches or the token is empty (query.rs:35).
-__global__ void descend_kernel(IndexView ix, const uint8_t* __restrict__ term_bytes,
-                               const uint64_t* __restrict__ term_byte_off, uint64_t n_qterms,
-                               uint32_t* __restrict__ qt_lo, uint32_t* __restrict__ qt_hi,
-                               uint32_t* __restrict__ qt_len) {
-  uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (t >= n_qterms) return;
-  const uint8_t* p = term_bytes + term_byte_off[t];
-  const uint8_t* e = term_bytes + term_byte_off[t + 1];
-  uint32_t len = (uint32_t)(e - p);
-  qt_len[t] = len;
-  uint32_t node = 0;
-  bool ok = len > 0;
-  while (ok && p < e) {
-    uint32_t c = *p++;
-    if (c >= 0x80) {                       // UTF-8 (validated on the host) -> Unicode scalar
-      int extra = (c >= 0xF0) ? 3 : (c >= 0xE0) ? 2 : 1;
-      c &= (0x3Fu >> extra);
-      for (int i = 0; i < extra && p < e; ++i) c = (c << 6) | (*p++ & 0x3Fu);
-    }
-    uint32_t lo = ix.node_edge_begin[node], hi = ix.node_edge_begin[node + 1];
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (ix.edge_char[mid] < c) lo = mid + 1; else hi = mid;
-    }
-    if (lo < ix.node_edge_begin[node + 1] && ix.edge_char[lo] == c) node = ix.edge_child[lo];
-    else ok = false;
-  }
-  qt_lo[t] = ok ? ix.node_term_lo[node] : 0u;
-  qt_hi[t] = ok ? ix.node_term_hi[node] : 0u;
-}
-
 // count_documents (index.rs:282-297) for every term: live occurrence count
 // df_live(t) = sum over the term's rows whose doc is live of sum_x tf[x]  (SURVEY §3.4 rule 2).
 template <int F>
@@ -501,236 +463,6 @@ __global__ void live_df_kernel(IndexView ix, unsigned long long* __restrict__ df
     n = warp_sum_u64(n);
     if (lane == 0) { df_live[t] = s; live_rows[t] = (uint32_t)n; }
   }
-}
-
-// Rank directory build (see IndexView::dir).  Pass 1: one warp-strided walk over the rows of every
-// dense term sets the doc bits.  Pass 2: one CTA per dense term turns the per-word popcounts into
-// exclusive prefix sums.
-__global__ void dir_bits_kernel(IndexView ix, const uint32_t* __restrict__ dense_terms, uint32_t n_dense, uint2* __restrict__ dir) {
-  for (uint32_t i = blockIdx.y; i < n_dense; i += gridDim.y) {
-    const uint32_t t = dense_terms[i];
-    const uint64_t a = ix.term_row_begin[t], b = ix.term_row_begin[t + 1];
-    uint2* d = dir + (size_t)i * ix.dir_words;
-    for (uint64_t r = a + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < b; r += (uint64_t)gridDim.x * blockDim.x) {
-      const uint32_t doc = row_doc(ix, r);
-      atomicOr(&d[doc >> 5].y, 1u << (doc & 31));
-    }
-  }
-}
-__global__ void __launch_bounds__(1024) dir_rank_kernel(uint32_t dir_words, uint2* __restrict__ dir) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_base;
-  uint2* d = dir + (size_t)blockIdx.x * dir_words;
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  for (uint32_t w0 = 0; w0 < dir_words; w0 += blockDim.x) {
-    const uint32_t w = w0 + threadIdx.x;
-    const uint32_t c = w < dir_words ? __popc(d[w].y) : 0u;
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t v = s_warp[threadIdx.x], x = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, x, o); if (threadIdx.x >= o) x += u; }
-      s_warp[threadIdx.x] = x - v;              // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    const uint32_t base = s_base;
-    if (w < dir_words) d[w].x = base + s_warp[threadIdx.x >> 5] + incl - c;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) s_base = base + s_warp[threadIdx.x >> 5] + incl;
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Planning
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t first_live_term(const IndexView& ix, uint32_t lo, uint32_t hi) {
-  // smallest t in [lo, hi) with df_live > 0, i.e. live_prefix[t+1] > live_prefix[lo]
-  uint32_t base = ix.live_prefix[lo];
-  uint32_t a = lo, b = hi;
-  while (a < b) {
-    uint32_t mid = (a + b) >> 1;
-    if (ix.live_prefix[mid + 1] > base) b = mid; else a = mid + 1;
-  }
-  return a;
-}
-
-// One thread per query.  Classifies the query by the number of live posting lists its terms
-// expand to (terms whose live df is 0 are skipped, query.rs:48):
-//   0 lists  -> empty result          1 list -> class S: one DIRECT segment (seg_s[q])
-//   >= 2     -> class G: qt_gcount[t] segments per query term, filled by gfill_kernel.
-__global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
-                                  const uint64_t* __restrict__ query_term_off,
-                                  const uint32_t* __restrict__ qt_lo, const uint32_t* __restrict__ qt_hi,
-                                  const uint32_t* __restrict__ qt_len, Seg* __restrict__ seg_s,
-                                  unsigned long long* __restrict__ s_tiles, unsigned long long* __restrict__ qt_gcount,
-                                  uint32_t* __restrict__ qt_q, unsigned long long* __restrict__ q_isg,
-                                  unsigned long long* __restrict__ q_grows, unsigned long long* __restrict__ stats) {
-  uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  unsigned long long st_rows = 0, st_live = 0, st_ptr = 0;
-  if (q < n_queries) {
-  uint64_t t0 = query_term_off[q], t1 = query_term_off[q + 1];
-  uint32_t nl = 0;
-  uint64_t rows = 0;
-  uint64_t single = t0;
-  for (uint64_t t = t0; t < t1; ++t) {
-    uint32_t lo = qt_lo[t], hi = qt_hi[t];
-    uint32_t c = ix.live_prefix[hi] - ix.live_prefix[lo];
-    if (c) single = t;
-    nl += c;
-    rows += ix.liverows_prefix[hi] - ix.liverows_prefix[lo];
-    qt_q[t] = (uint32_t)q;
-  }
-  Seg s;
-  s.row_begin = 0; s.n_rows = 0; s.q = (uint32_t)q; s.term = 0; s.qlen = 0; s.qti = 0;
-  s.mode = MODE_DIRECT; s.pad = 0; s.slot = 0;
-  unsigned long long tiles = 0;
-  if (nl == 1) {
-    uint32_t term = first_live_term(ix, qt_lo[single], qt_hi[single]);
-    uint64_t a = ix.term_row_begin[term], b = ix.term_row_begin[term + 1];
-    s.row_begin = a; s.n_rows = (uint32_t)(b - a); s.term = term; s.qlen = qt_len[single];
-    s.qti = (uint16_t)(single - t0);
-    tiles = ((b + TILE_ROWS - 1) / TILE_ROWS) - (a / TILE_ROWS);
-    // the launch's row statistics are known without touching a row:
-    st_rows = b - a;                       // rows streamed
-    st_live = ix.term_live_rows[term];     // rows whose doc is live = score() evaluations
-    st_ptr = ix.term_df_live[term];        // reference DocumentPointer visits (sum of multiplicities)
-  }
-  seg_s[q] = s;
-  s_tiles[q] = tiles;
-  bool g = nl >= 2;
-  q_isg[q] = g ? 1ull : 0ull;
-  q_grows[q] = g ? rows : 0ull;
-  for (uint64_t t = t0; t < t1; ++t)
-    qt_gcount[t] = g ? (unsigned long long)(ix.live_prefix[qt_hi[t]] - ix.live_prefix[qt_lo[t]]) : 0ull;
-  }
-  st_rows = warp_sum_u64(st_rows); st_live = warp_sum_u64(st_live); st_ptr = warp_sum_u64(st_ptr);
-  if ((threadIdx.x & 31) == 0 && st_rows) {
-    atomicAdd(&stats[ST_ROWS_STREAMED], st_rows);
-    atomicAdd(&stats[ST_ROWS_SCORED], st_live);
-    atomicAdd(&stats[ST_POINTER_VISITS], st_ptr);
-  }
-}
-
-// One warp per query term of a class-G query: writes one SECONDARY segment per live expanded
-// term, in expansion order, and elects the query's largest list (atomicMax on rows<<32|seg).
-__global__ void gfill_kernel(IndexView ix, uint64_t n_qterms, const uint64_t* __restrict__ query_term_off,
-                             const uint32_t* __restrict__ qt_lo, const uint32_t* __restrict__ qt_hi,
-                             const uint32_t* __restrict__ qt_len, const uint32_t* __restrict__ qt_q,
-                             const unsigned long long* __restrict__ qt_gcount, const unsigned long long* __restrict__ qt_goff,
-                             Seg* __restrict__ seg_g, unsigned long long* __restrict__ g_tiles,
-                             unsigned long long* __restrict__ q_prim, unsigned long long* __restrict__ stats) {
-  int lane = threadIdx.x & 31;
-  uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  unsigned long long st_rows = 0, st_live = 0, st_ptr = 0;
-  for (uint64_t t = warp; t < n_qterms; t += nwarps) {
-    if (qt_gcount[t] == 0) continue;
-    uint32_t lo = qt_lo[t], hi = qt_hi[t], q = qt_q[t];
-    uint32_t qlen = qt_len[t];
-    uint16_t qti = (uint16_t)(t - query_term_off[q]);
-    uint64_t out = qt_goff[t];
-    unsigned long long best = 0;
-    for (uint32_t base = lo; base < hi; base += 32) {
-      uint32_t term = base + lane;
-      bool live = term < hi && ix.term_df_live[term] > 0;
-      uint32_t m = __ballot_sync(0xffffffffu, live);
-      if (live) {
-        uint64_t idx = out + __popc(m & ((1u << lane) - 1u));
-        uint64_t a = ix.term_row_begin[term], b = ix.term_row_begin[term + 1];
-        Seg s;
-        s.row_begin = a; s.n_rows = (uint32_t)(b - a); s.q = q; s.term = term; s.qlen = qlen;
-        s.qti = qti; s.mode = MODE_SECONDARY; s.pad = 0; s.slot = 0;
-        seg_g[idx] = s;
-        g_tiles[idx] = ((b + TILE_ROWS - 1) / TILE_ROWS) - (a / TILE_ROWS);
-        unsigned long long cand = ((unsigned long long)(b - a) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
-        best = max(best, cand);
-        st_rows += b - a; st_live += ix.term_live_rows[term]; st_ptr += ix.term_df_live[term];
-      }
-      out += __popc(m);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = max(best, (unsigned long long)shfl_u64(best, lane ^ o));
-    if (lane == 0 && best) atomicMax(&q_prim[q], best);
-  }
-  st_rows = warp_sum_u64(st_rows); st_live = warp_sum_u64(st_live); st_ptr = warp_sum_u64(st_ptr);
-  if (lane == 0 && st_rows) {
-    atomicAdd(&stats[ST_ROWS_STREAMED], st_rows);
-    atomicAdd(&stats[ST_ROWS_SCORED], st_live);
-    atomicAdd(&stats[ST_POINTER_VISITS], st_ptr);
-  }
-}
-
-// One thread per query: promote the elected list to PRIMARY and bound the side-path records:
-// every secondary row + at most one primary row per secondary doc.
-__global__ void gprimary_kernel(uint64_t n_queries, uint32_t doc_bits, const unsigned long long* __restrict__ q_isg,
-                                const unsigned long long* __restrict__ q_grows,
-                                const unsigned long long* __restrict__ q_prim, Seg* __restrict__ seg_g,
-                                unsigned long long* __restrict__ q_recbound, unsigned long long* __restrict__ q_nbins,
-                                uint8_t* __restrict__ q_scheme, uint8_t* __restrict__ q_shift,
-                                const uint64_t* __restrict__ query_term_off,
-                                const unsigned long long* __restrict__ qt_goff,
-                                unsigned long long* __restrict__ q_gsegoff, unsigned long long* __restrict__ q_bmwords,
-                                uint32_t bitmap_words, unsigned long long* __restrict__ qmax) {
-  uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (q > n_queries) return;
-  q_gsegoff[q] = qt_goff[query_term_off[q]];   // qt_goff has n_qterms + 1 entries
-  if (q == n_queries) return;
-  unsigned long long bound = 0, nbins = 0, bmw = 0;
-  uint8_t scheme = 0, shift = 0;
-  if (q_isg[q]) {
-    unsigned long long p = q_prim[q];
-    uint32_t idx = 0xFFFFFFFFu - (uint32_t)(p & 0xFFFFFFFFull);
-    unsigned long long prows = p >> 32;
-    unsigned long long rows = q_grows[q], secondary = rows - prows;
-    if (secondary * 16ull >= rows) {
-      // exact scheme: the record count is only known after the marking pass; plan with an estimate
-      scheme = 1;
-      bound = rows / 2 + 1024;
-      bmw = bitmap_words;
-    } else {
-      // primary scheme: every secondary row + at most one primary row per secondary doc
-      seg_g[idx].mode = MODE_PRIMARY;
-      bound = 2ull * secondary;
-      // row mask: 4 words per tile the primary list touches
-      const unsigned long long a = seg_g[idx].row_begin, e = a + seg_g[idx].n_rows;
-      bmw = 4ull * ((e + TILE_ROWS - 1) / TILE_ROWS - a / TILE_ROWS) + 12ull;     // + pads: the scoring loop reads masks 2 tiles ahead
-    }
-    // doc-range bins of width 2^shift sized for ~8 records each (a warp window holds 32)
-    const unsigned long long n_docs_pow = 1ull << doc_bits;
-    unsigned long long want = bound / 8 + 1;                 // number of bins wanted
-    uint32_t sh = doc_bits;
-    while (sh > 0 && (n_docs_pow >> sh) < want) --sh;
-    shift = (uint8_t)sh;
-    nbins = (n_docs_pow >> sh);
-  }
-  q_recbound[q] = bound;
-  q_bmwords[q] = bmw;
-  if (bound) { atomicMax(&qmax[0], bound); atomicMax(&qmax[1], bmw); }     // largest single query (host: capacities)
-  q_nbins[q] = nbins;
-  q_scheme[q] = scheme;
-  q_shift[q] = shift;
-}
-
-// Per round: slot = rank of the query among the round's class-G queries (key of the sorted fallback).
-// Also writes the tile count of every list the MARKING pass walks (all but the primary lists): its
-// prefix sum is the marking pass's own tile space, so that its warps share that work evenly.
-__global__ void gslot_kernel(Seg* __restrict__ seg_g, uint64_t seg_begin, uint64_t seg_end,
-                             const unsigned long long* __restrict__ q_gidx, const uint8_t* __restrict__ q_scheme,
-                             uint32_t q_begin, const unsigned long long* __restrict__ g_tiles,
-                             unsigned long long* __restrict__ g_mtiles) {
-  uint64_t i = seg_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i > seg_end) return;
-  if (i == seg_end) { g_mtiles[i] = 0ull; return; }
-  const uint32_t q = seg_g[i].q;
-  seg_g[i].slot = (uint32_t)(q_gidx[q] - q_gidx[q_begin]);
-  if (q_scheme[q]) seg_g[i].mode = MODE_MULTI;
-  g_mtiles[i] = seg_g[i].mode == MODE_PRIMARY ? 0ull : g_tiles[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1768,34 +1500,6 @@ __global__ void __launch_bounds__(CTA_THREADS) binfold_kernel(const __grid_const
     b += nb_take;
   }
   if (acc.q != NONE) acc.flush(P.out, false, lane);
-}
-
-// One warp per query: merge the partial top-k lists into the final (score desc, doc asc) top-k.
-__global__ void __launch_bounds__(CTA_THREADS) finalize_kernel(Outputs o, uint64_t n_queries) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  if (o.k == 0) return;
-  for (uint64_t q = w; q < n_queries; q += W) {
-    uint32_t p = o.part_head[q];
-    if (p == NONE) continue;
-    WarpAcc acc;
-    acc.reset((uint32_t)q);
-    while (p != NONE) {
-      uint32_t n = o.part_n[p];
-      bool v = lane < (int)n;
-      uint32_t d = v ? o.part_doc[(size_t)p * o.k + lane] : NONE;
-      double s = v ? o.part_score[(size_t)p * o.k + lane] : -1.0;
-      acc.insert_candidates(v && better(s, d, acc.thr_s, acc.thr_d), d, s, lane, (int)o.k);
-      p = o.part_next[p];
-    }
-    uint32_t ntop = (uint32_t)min((unsigned long long)o.k, o.n_results[q]);
-    if (lane < (int)ntop) {
-      o.topk_doc[(size_t)q * o.k + lane] = acc.td;
-      o.topk_score[(size_t)q * o.k + lane] = acc.ts;
-    }
-    if (lane == 0) o.topk_n[q] = ntop;
-  }
 }
 
 }  // namespace pbk
