@@ -248,6 +248,13 @@ typedef struct pb_batch_stats {
   float ms_total;             /* CUDA-event time of the last pb_batch_run on its stream */
   float ms_descend, ms_plan, ms_score, ms_side, ms_finalize;
   uint32_t score_launches;    /* launches of the scoring kernel inside ms_score */
+  float ms_gather;            /* the ncclAllGather of the result block (0 without pb_batch_set_gather); inside ms_total */
+  /* CUDA-event time of each launch class of the multi-list side path, summed over its rounds (inside ms_side) */
+  float ms_side_mark, ms_side_score, ms_side_fold;
+  float ms_union;             /* the dense union kernel (ZeroToOne, union-heavy queries); inside ms_side */
+  uint64_t rows_streamed_side;  /* posting rows read by the class-G scoring launches (inside ms_side_score) */
+  uint64_t rows_streamed_union; /* posting rows read by the union kernel */
+  uint64_t union_queries;       /* queries answered by the union kernel */
 } pb_batch_stats;
 int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out);
 /* Stats of the last pb_query_batch / pb_query_full call on this index. */
@@ -258,6 +265,58 @@ int pb_index_last_stats(pb_index* ix, pb_batch_stats* out);
  * PB_ERR_CAPACITY when cap is too small (nothing useful written). */
 int pb_query_full(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint32_t* out_query,
                   uint32_t* out_doc, double* out_score, uint64_t* n_total);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU.  Index::query is a pure function of &self (src/query.rs:21-22), so a batch
+ * shards by QUERY: every GPU holds a replica of the image, rank r scores its own block of queries,
+ * and the only exchange is ONE ncclAllGather of the packed per-query result blocks, issued by the
+ * library on the batch's own stream right behind its last kernel.  NCCL is bound at run time
+ * (libnccl.so.2 via dlopen); without it these entry points return PB_ERR_UNSUPPORTED.
+ *
+ * Two forms:
+ *  (1) one PROCESS per GPU (torchrun / MPI / any launcher): rank 0 calls pb_comm_unique_id, the id
+ *      reaches the other ranks over any host channel, every rank calls pb_comm_create, attaches the
+ *      communicator to its batch with pb_batch_set_gather, and from then on pb_batch_run ends with
+ *      the gather (inside ms_total); pb_batch_fetch_gathered returns all ranks' results.
+ *  (2) one process, several devices: pb_group_create replicates an image on the listed devices
+ *      (ncclCommInitAll) and pb_group_query_batch runs a whole batch across them.
+ * Every rank must use the same slot_queries (>= its own n_queries) and top_k: rank r's query i
+ * is global query r * slot_queries + i.  As with any collective, a rank that fails before the
+ * gather leaves its peers waiting in it; pb_group_query_batch avoids that by gathering only after
+ * every member has finished its kernels.
+ * ---------------------------------------------------------------------------------------- */
+#define PB_COMM_ID_BYTES 128u
+typedef struct pb_comm pb_comm;   /* one rank of an NCCL communicator */
+typedef struct pb_group pb_group; /* one process: an image replica + communicator rank per device */
+int pb_comm_unique_id(uint8_t* id /* [PB_COMM_ID_BYTES] */);
+int pb_comm_create(const uint8_t* id, int rank, int world, int device, pb_comm** out);
+int pb_comm_info(const pb_comm* c, int* rank, int* world, int* nccl_version);
+void pb_comm_destroy(pb_comm* c);
+
+/* Attach (comm != NULL) or detach (NULL) the gather.  The communicator must outlive the batch. */
+int pb_batch_set_gather(pb_batch* b, pb_comm* comm, uint64_t slot_queries);
+/* Re-stage a new query batch into an existing pb_batch (keeps its stream, workspace and gather). */
+int pb_batch_reload(pb_batch* b, const pb_query_batch_desc* q);
+/* The stages of pb_batch_run separately: kernels only / enqueue the gather / wait for the stream. */
+int pb_batch_run_local(pb_batch* b);
+int pb_batch_gather(pb_batch* b);
+int pb_batch_sync(pb_batch* b);
+/* Results of ALL ranks in global query order: the first n_total of world * slot_queries queries. */
+int pb_batch_fetch_gathered(pb_batch* b, uint64_t n_total, pb_query_results* out);
+/* DEVICE view of the gathered blocks: rank r's packed block starts at block0 + r * block_bytes and
+ * is laid out for slot_queries queries as [n_results u64][doc_digest u64][score_digest u64]
+ * [topk_score f64 x k][topk_doc u32 x k][topk_n u32], each array slot_queries long. */
+int pb_batch_device_gathered(pb_batch* b, const void** block0, uint64_t* block_bytes, uint64_t* slot_queries);
+
+int pb_group_create(const pb_index_image* image, const int* devices, int n, pb_group** out);
+int pb_group_size(const pb_group* g);
+int pb_group_set_live_state(pb_group* g, const uint32_t* removed_ords, uint64_t n_removed, uint64_t n_live_docs,
+                            const double* field_avg);
+/* Queries are cut into contiguous blocks of ceil(n_queries / n) per member; `out` receives all
+ * n_queries results in the caller's order (same layout as pb_query_batch). */
+int pb_group_query_batch(pb_group* g, const pb_query_batch_desc* q, pb_query_results* out);
+int pb_group_member_stats(pb_group* g, int member, pb_batch_stats* out);
+void pb_group_destroy(pb_group* g);
 
 /* Pinned host memory for the buffers of pb_query_batch (optional; any host memory works). */
 void* pb_host_alloc(size_t bytes);

@@ -78,7 +78,10 @@ class BatchStats(C.Structure):
                 ("results_emitted", C.c_uint64), ("pointer_visits", C.c_uint64), ("gpu_launches", C.c_uint32),
                 ("side_rounds", C.c_uint32), ("ms_total", C.c_float), ("ms_descend", C.c_float),
                 ("ms_plan", C.c_float), ("ms_score", C.c_float), ("ms_side", C.c_float),
-                ("ms_finalize", C.c_float), ("score_launches", C.c_uint32)]
+                ("ms_finalize", C.c_float), ("score_launches", C.c_uint32), ("ms_gather", C.c_float),
+                ("ms_side_mark", C.c_float), ("ms_side_score", C.c_float), ("ms_side_fold", C.c_float),
+                ("ms_union", C.c_float), ("rows_streamed_side", C.c_uint64), ("rows_streamed_union", C.c_uint64),
+                ("union_queries", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -93,7 +96,13 @@ EXPORTS = [
     "pb_image_save", "pb_image_load", "pb_image_file_image", "pb_image_file_free", "pb_query_batch", "pb_batch_create", "pb_batch_run",
     "pb_batch_fetch", "pb_batch_destroy", "pb_batch_device_results", "pb_batch_get_stats", "pb_index_last_stats", "pb_query_full",
     "pb_host_alloc", "pb_host_free", "pb_last_error", "pb_version",
+    "pb_comm_unique_id", "pb_comm_create", "pb_comm_info", "pb_comm_destroy",
+    "pb_batch_set_gather", "pb_batch_reload", "pb_batch_run_local", "pb_batch_gather", "pb_batch_sync",
+    "pb_batch_fetch_gathered", "pb_batch_device_gathered",
+    "pb_group_create", "pb_group_size", "pb_group_set_live_state", "pb_group_query_batch", "pb_group_member_stats",
+    "pb_group_destroy",
 ]
+PB_COMM_ID_BYTES = 128
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(_HERE, "_lib", "libprobly_b200.so")   # PB_LIB_PATH: tuning variants
@@ -151,6 +160,23 @@ def lib() -> C.CDLL:
         "pb_host_free": (None, [vp]),
         "pb_last_error": (C.c_char_p, []),
         "pb_version": (C.c_char_p, []),
+        "pb_comm_unique_id": (i32, [vp]),
+        "pb_comm_create": (i32, [vp, i32, i32, i32, P(vp)]),
+        "pb_comm_info": (i32, [vp, P(i32), P(i32), P(i32)]),
+        "pb_comm_destroy": (None, [vp]),
+        "pb_batch_set_gather": (i32, [vp, vp, u64]),
+        "pb_batch_reload": (i32, [vp, P(QueryBatchDesc)]),
+        "pb_batch_run_local": (i32, [vp]),
+        "pb_batch_gather": (i32, [vp]),
+        "pb_batch_sync": (i32, [vp]),
+        "pb_batch_fetch_gathered": (i32, [vp, u64, P(QueryResults)]),
+        "pb_batch_device_gathered": (i32, [vp, P(vp), P(u64), P(u64)]),
+        "pb_group_create": (i32, [P(IndexImage), P(i32), i32, P(vp)]),
+        "pb_group_size": (i32, [vp]),
+        "pb_group_set_live_state": (i32, [vp, vp, u64, u64, vp]),
+        "pb_group_query_batch": (i32, [vp, P(QueryBatchDesc), P(QueryResults)]),
+        "pb_group_member_stats": (i32, [vp, i32, P(BatchStats)]),
+        "pb_group_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

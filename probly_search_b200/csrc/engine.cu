@@ -21,6 +21,7 @@
 
 #include "common.hpp"
 #include "field_ops.hpp"
+#include "group.hpp"
 #include "plan_kernels.cuh"
 
 using namespace pbk;
@@ -123,6 +124,7 @@ struct pb_index {
   std::vector<uint64_t> h_term_row_begin, h_df_live;
   uint64_t n_live = 0, n_removed = 0;
   double avg[4] = {0, 0, 0, 0};
+  uint64_t live_epoch = 0;       // bumped by every pb_index_set_live_state: staged batches rebuild their BM25 table
   std::mutex mu;                 // guards `scratch`
   pb_batch* scratch = nullptr;   // reused by pb_query_batch / pb_query_full / expand_term
 
@@ -152,6 +154,7 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
   CU(cudaMemcpy(ix->removed.p, bitmap_words, words * sizeof(uint32_t), cudaMemcpyHostToDevice));
   ix->n_removed = n_removed;
   ix->n_live = n_live;
+  ++ix->live_epoch;
   for (uint32_t f = 0; f < ix->F; ++f) ix->avg[f] = avg[f];
   const size_t NT = ix->n_terms;
   CU(ix->term_df_live.ensure(NT + 1));
@@ -193,7 +196,7 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
 struct pb_batch {
   pb_index* ix = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[9] = {};
   uint64_t Q = 0, NT = 0;
   uint32_t scorer = 0, k = 0;
   double k1 = 1.2, b = 0.75, boost[4] = {1, 1, 1, 1};
@@ -216,10 +219,20 @@ struct pb_batch {
   DBuf<ull> s_tiles, s_tile_off, g_tiles, g_tile_off, g_mtiles, g_mtile_off;
   DBuf<Seg> seg_s, seg_g;
   DBuf<uint8_t> cub_temp;
-  // outputs
-  DBuf<ull> n_results, doc_digest, score_digest;
-  DBuf<uint32_t> topk_n, topk_doc;
-  DBuf<double> topk_score;
+  // outputs: ONE packed block laid out for `slot` >= Q queries
+  //   [n_results u64 x slot][doc_digest u64 x slot][score_digest u64 x slot][topk_score f64 x slot*k]
+  //   [topk_doc u32 x slot*k][topk_n u32 x slot]   (padded to 16 bytes)
+  // so that the multi-GPU exchange is a single ncclAllGather of the block.
+  DBuf<uint8_t> res, gath;
+  uint64_t slot = 0;            // queries the block is laid out for (= Q unless a gather asks for more)
+  uint64_t want_slot = 0;       // pb_batch_set_gather: the per-rank slot every rank agreed on
+  size_t block_bytes = 0;
+  ull *n_results = nullptr, *doc_digest = nullptr, *score_digest = nullptr;
+  uint32_t *topk_n = nullptr, *topk_doc = nullptr;
+  double* topk_score = nullptr;
+  pb_comm* comm = nullptr;      // not owned
+  bool gather_pending = false, gathered = false;
+  uint64_t tab_epoch = 0;       // ix->live_epoch the BM25 table was built for
   // partial lists + counters
   DBuf<uint32_t> part_head, part_next, part_n, part_doc, counters;   // counters: [0] part_count [1] rec_count [2] error
   DBuf<double> part_score;
@@ -236,10 +249,25 @@ struct pb_batch {
   std::vector<ull> h_recoff, h_binoff, h_gidx, h_gsegoff, h_gtileoff, h_bmoff;
   bool h_full = false;           // the vectors above hold every entry (else only [0] and [Q])
   pb_batch_stats st{};
+  uint32_t launches = 0;         // kernels enqueued by the current run
+  // per-launch-class timing inside the side path: pairs of pooled events, summed by batch_finish
+  std::vector<cudaEvent_t> rev;
+  size_t rev_used = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> rev_span[4];   // 0 mark, 1 score (class G), 2 fold (bin fold + sorted fallback), 3 union
+  int rev_begin() {
+    if (rev_used == rev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return -1; rev.push_back(e); }
+    if (cudaEventRecord(rev[rev_used], stream) != cudaSuccess) return -1;
+    return (int)rev_used++;
+  }
+  void rev_end(int cls, int e0) {
+    int e1 = rev_begin();
+    if (e0 >= 0 && e1 >= 0) rev_span[cls].push_back({(uint32_t)e0, (uint32_t)e1});
+  }
 
   ~pb_batch() {
     if (ix) cudaSetDevice(ix->device);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : rev) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -279,6 +307,28 @@ __global__ void gather_tileoff_kernel(uint64_t n, const ull* __restrict__ q_gseg
                                       const ull* __restrict__ g_tile_off, ull* __restrict__ q_gtileoff) {
   uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (q < n) q_gtileoff[q] = g_tile_off[q_gsegoff[q]];
+}
+
+struct ResLayout { size_t n, dd, sd, ts, td, tn, bytes; };
+ResLayout res_layout(uint64_t slot, uint32_t k) {
+  const size_t kk = std::max<uint32_t>(k, 1);
+  ResLayout L;
+  L.n = 0; L.dd = L.n + slot * 8; L.sd = L.dd + slot * 8; L.ts = L.sd + slot * 8;
+  L.td = L.ts + slot * kk * 8; L.tn = L.td + slot * kk * 4;
+  L.bytes = (L.tn + slot * 4 + 15) & ~(size_t)15;
+  return L;
+}
+// (re)lays the packed result block out for max(Q, want_slot) queries
+int batch_layout_results(pb_batch* b) {
+  const uint64_t slot = std::max<uint64_t>(std::max<uint64_t>(b->Q, b->want_slot), 1);
+  const ResLayout L = res_layout(slot, b->k);
+  CU(b->res.ensure(L.bytes));
+  b->slot = slot; b->block_bytes = L.bytes;
+  uint8_t* p = b->res.p;
+  b->n_results = (ull*)(p + L.n); b->doc_digest = (ull*)(p + L.dd); b->score_digest = (ull*)(p + L.sd);
+  b->topk_score = (double*)(p + L.ts); b->topk_doc = (uint32_t*)(p + L.td); b->topk_n = (uint32_t*)(p + L.tn);
+  if (b->comm) CU(b->gath.ensure(L.bytes * (size_t)pbg::comm_world(b->comm)));
+  return PB_OK;
 }
 
 double bm25_tf_host(double k1, double b, double avg, uint32_t tf, uint32_t fl) {
@@ -373,10 +423,7 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   CU(b->q_scheme.ensure(Q + 2)); CU(b->q_shift.ensure(Q + 2)); CU(b->xcount.ensure(4)); CU(b->q_bmwords.ensure(Q + 2)); CU(b->q_bmoff.ensure(Q + 2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
   CU(b->s_tiles.ensure(Q + 2)); CU(b->s_tile_off.ensure(Q + 2));
   CU(b->seg_s.ensure(Q + 1));
-  CU(b->n_results.ensure(Q + 1)); CU(b->doc_digest.ensure(Q + 1)); CU(b->score_digest.ensure(Q + 1));
-  CU(b->topk_n.ensure(Q + 1));
-  CU(b->topk_doc.ensure(Q * std::max<uint32_t>(b->k, 1) + 1));
-  CU(b->topk_score.ensure(Q * std::max<uint32_t>(b->k, 1) + 1));
+  RC(batch_layout_results(b));
   CU(b->part_head.ensure(Q + 1));
   CU(b->counters.ensure(8));
   CU(b->stats.ensure(2 * ST_COUNT));
@@ -385,6 +432,7 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   }
   CU(b->full_count.ensure(2));
   if (b->scorer == PB_SCORER_BM25) RC(batch_build_table(b));
+  b->tab_epoch = ix->live_epoch;
   CU(cudaStreamSynchronize(b->stream));   // caller buffers may be reused after return
   b->loaded = true;
   b->ran = false;
@@ -473,9 +521,18 @@ int fetch_prefix_arrays(pb_batch* b) {
   return PB_OK;
 }
 
-int batch_run(pb_batch* b) {
+// Stage 1 of a run: every kernel of the batch up to the merged top-k, enqueued on the batch's stream
+// (with the host round trips the planning needs).  ev[0] .. ev[5] bracket its phases.
+int batch_compute(pb_batch* b) {
   pb_index* ix = b->ix;
   if (!b->loaded) { pb::set_error("pb_batch_run: batch not loaded"); return PB_ERR_INVALID; }
+  b->ran = false; b->gathered = false; b->gather_pending = false;
+  b->rev_used = 0;
+  for (auto& v : b->rev_span) v.clear();
+  if (b->scorer == PB_SCORER_BM25 && b->tab_epoch != ix->live_epoch) {     // pb_index_set_live_state since staging: new avg
+    RC(batch_build_table(b));
+    b->tab_epoch = ix->live_epoch;
+  }
   CU(cudaSetDevice(ix->device));
   cudaStream_t st = b->stream;
   const uint64_t Q = b->Q, NT = b->NT;
@@ -487,16 +544,17 @@ int batch_run(pb_batch* b) {
   if (ix->n_rows_padded >= 0xFFFFFFFFull) { pb::set_error("index has more than 2^32 posting rows"); return PB_ERR_UNSUPPORTED; }
 
   CU(cudaEventRecord(b->ev[0], st));
-  CU(cudaMemsetAsync(b->n_results.p, 0, (Q + 1) * sizeof(ull), st));
-  CU(cudaMemsetAsync(b->doc_digest.p, 0, (Q + 1) * sizeof(ull), st));
-  CU(cudaMemsetAsync(b->score_digest.p, 0, (Q + 1) * sizeof(ull), st));
-  CU(cudaMemsetAsync(b->topk_n.p, 0, (Q + 1) * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(b->res.p, 0, b->block_bytes, st));      // counts, digests, top-k: one packed block
   CU(cudaMemsetAsync(b->part_head.p, 0xFF, (Q + 1) * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(b->stats.p, 0, 2 * ST_COUNT * sizeof(ull), st));
   CU(cudaMemsetAsync(b->q_prim.p, 0, (Q + 2) * sizeof(ull), st));
   CU(cudaMemsetAsync(b->full_count.p, 0, 2 * sizeof(ull), st));
-  if (Q == 0) { b->ran = true; return PB_OK; }
+  if (Q == 0) {
+    for (int i = 1; i <= 5; ++i) CU(cudaEventRecord(b->ev[i], st));
+    b->launches = 0;
+    return PB_OK;
+  }
 
   IndexView view = ix->view();
   // ---- trie descent + prefix expansion ---------------------------------------------------
@@ -615,8 +673,8 @@ int batch_run(pb_batch* b) {
   ScoreParams P;
   std::memset(&P, 0, sizeof(P));
   P.ix = view;
-  P.out.n_results = b->n_results.p; P.out.doc_digest = b->doc_digest.p; P.out.score_digest = b->score_digest.p;
-  P.out.topk_n = b->topk_n.p; P.out.topk_doc = b->topk_doc.p; P.out.topk_score = b->topk_score.p; P.out.k = k;
+  P.out.n_results = b->n_results; P.out.doc_digest = b->doc_digest; P.out.score_digest = b->score_digest;
+  P.out.topk_n = b->topk_n; P.out.topk_doc = b->topk_doc; P.out.topk_score = b->topk_score; P.out.k = k;
   P.out.part_head = b->part_head.p; P.out.part_next = b->part_next.p; P.out.part_n = b->part_n.p;
   P.out.part_doc = b->part_doc.p; P.out.part_score = b->part_score.p; P.out.part_count = b->counters.p + 0;
   P.out.part_cap = (uint32_t)part_cap;
@@ -696,7 +754,7 @@ int batch_run(pb_batch* b) {
       PM.tile_off = (const uint64_t*)b->g_mtile_off.p;
       int mgrid = ix->sm_count * 8;            // the size of the marking tile space is only known on the device
       CU(cudaMemsetAsync(b->xcount.p, 0, 2 * sizeof(ull), st));
-      RC(launch_mark(b, PM, mgrid, 0));
+      { const int e0 = b->rev_begin(); RC(launch_mark(b, PM, mgrid, 0)); b->rev_end(0, e0); }
       launches += 2;
       ull h_x[2] = {0, 0};
       CU(cudaMemcpyAsync(h_x, b->xcount.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -751,7 +809,7 @@ int batch_run(pb_batch* b) {
       } else {
         CU(cudaMemsetAsync(b->bin_off.p, 0, (n_bins + 2) * sizeof(uint32_t), st));
       }
-      RC(launch_score(b, P, true, tiles));
+      { const int e0 = b->rev_begin(); RC(launch_score(b, P, true, tiles)); b->rev_end(1, e0); }
       ++launches;
       if (need) {
         // records of bins that overflow a warp window go through the legacy sorted path
@@ -770,6 +828,7 @@ int batch_run(pb_batch* b) {
           CU(b->rec_key2.ensure(legacy_cap)); CU(b->rec_val2.ensure(legacy_cap));
         }
         P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)legacy_cap;
+        const int ef0 = b->rev_begin();
         RC(launch_binfold(b, P, n_bins));
         launches += 2;
         if (h_over) {
@@ -787,6 +846,7 @@ int batch_run(pb_batch* b) {
           launches += 2 + (uint32_t)((end_bit + 7) / 8);
           S.legacy_records += h_over;
         }
+        b->rev_end(2, ef0);
       }
       RC(clear_marks(true));
       CU(cudaMemsetAsync(b->counters.p + 1, 0, sizeof(uint32_t), st));
@@ -804,12 +864,35 @@ int batch_run(pb_batch* b) {
     ++launches;
   }
   CU(cudaEventRecord(b->ev[5], st));
+  b->launches = launches;
+  return PB_OK;
+}
+
+// Stage 2 (multi-GPU only): ONE ncclAllGather of the packed result block on the batch's stream, right
+// behind the last kernel — the next run's memsets are ordered after it on the same stream.
+int batch_gather(pb_batch* b) {
+  if (!b->comm) { pb::set_error("pb_batch_gather: no communicator attached (pb_batch_set_gather)"); return PB_ERR_INVALID; }
+  CU(cudaSetDevice(b->ix->device));
+  CU(cudaEventRecord(b->ev[6], b->stream));
+  RC(pbg::comm_allgather(b->comm, b->res.p, b->gath.p, b->block_bytes, b->stream));
+  CU(cudaEventRecord(b->ev[7], b->stream));
+  b->gather_pending = true;
+  return PB_OK;
+}
+
+// Stage 3: wait for the stream, read the device-side counters and error flags, fill the stats.
+int batch_finish(pb_batch* b) {
+  pb_index* ix = b->ix;
+  cudaStream_t st = b->stream;
+  pb_batch_stats& S = b->st;
+  CU(cudaSetDevice(ix->device));
   ull h_stats[2 * ST_COUNT];
   uint32_t h_cnt[4] = {0, 0, 0, 0};
   ull h_full[2] = {0, 0};
   CU(cudaMemcpyAsync(h_full, b->full_count.p, sizeof(h_full), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h_stats, b->stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h_cnt, b->counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(b->ev[8], st));
   CU(cudaStreamSynchronize(st));
   if (h_cnt[2] & 1u) { pb::set_error("internal: partial top-k list overflow"); return PB_ERR_INVALID; }
   if (h_cnt[2] & 2u) { pb::set_error("internal: side-path record buffer overflow"); return PB_ERR_INVALID; }
@@ -821,16 +904,37 @@ int batch_run(pb_batch* b) {
   S.rows_diverted = h_stats[ST_COUNT + ST_ROWS_DIVERTED];
   S.rows_streamed_direct = h_stats[ST_ROWS_STREAMED];
   S.results_emitted = h_full[1];
-  S.gpu_launches = launches;
+  S.gpu_launches = b->launches + (b->gather_pending ? 1u : 0u);
   float ms = 0;
-  CU(cudaEventElapsedTime(&ms, b->ev[0], b->ev[5])); S.ms_total = ms;
+  CU(cudaEventElapsedTime(&ms, b->ev[0], b->ev[8])); S.ms_total = ms;
   CU(cudaEventElapsedTime(&ms, b->ev[0], b->ev[1])); S.ms_descend = ms;
   CU(cudaEventElapsedTime(&ms, b->ev[1], b->ev[2])); S.ms_plan = ms;
   CU(cudaEventElapsedTime(&ms, b->ev[2], b->ev[3])); S.ms_score = ms;
   CU(cudaEventElapsedTime(&ms, b->ev[3], b->ev[4])); S.ms_side = ms;
   CU(cudaEventElapsedTime(&ms, b->ev[4], b->ev[5])); S.ms_finalize = ms;
+  {
+    float* dst[4] = {&S.ms_side_mark, &S.ms_side_score, &S.ms_side_fold, &S.ms_union};
+    for (int c = 0; c < 4; ++c) {
+      double acc = 0;
+      for (auto& pr : b->rev_span[c]) { CU(cudaEventElapsedTime(&ms, b->rev[pr.first], b->rev[pr.second])); acc += ms; }
+      *dst[c] = (float)acc;
+    }
+  }
+  S.rows_streamed_side = h_stats[ST_COUNT + ST_ROWS_STREAMED];
+  S.ms_gather = 0.f;
+  if (b->gather_pending) {
+    CU(cudaEventElapsedTime(&ms, b->ev[6], b->ev[7])); S.ms_gather = ms;
+    b->gathered = true;
+    b->gather_pending = false;
+  }
   b->ran = true;
   return PB_OK;
+}
+
+int batch_run(pb_batch* b) {
+  RC(batch_compute(b));
+  if (b->comm) RC(batch_gather(b));
+  return batch_finish(b);
 }
 
 int batch_new(pb_index* ix, pb_batch** out) {
@@ -838,7 +942,7 @@ int batch_new(pb_index* ix, pb_batch** out) {
   pb_batch* b = new pb_batch();
   b->ix = ix;
   cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->ev[i]);
+  for (int i = 0; i < 9 && e == cudaSuccess; ++i) e = cudaEventCreate(&b->ev[i]);
   if (e != cudaSuccess) { delete b; pb::set_error("stream/event creation failed: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
   *out = b;
   return PB_OK;
@@ -850,12 +954,12 @@ int batch_fetch(pb_batch* b, pb_query_results* o) {
   const uint64_t Q = b->Q;
   cudaStream_t st = b->stream;
   if (Q) {
-    if (o->n_results) CU(cudaMemcpyAsync(o->n_results, b->n_results.p, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    if (o->doc_digest) CU(cudaMemcpyAsync(o->doc_digest, b->doc_digest.p, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    if (o->score_digest) CU(cudaMemcpyAsync(o->score_digest, b->score_digest.p, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
-    if (o->topk_n) CU(cudaMemcpyAsync(o->topk_n, b->topk_n.p, Q * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    if (b->k && o->topk_doc) CU(cudaMemcpyAsync(o->topk_doc, b->topk_doc.p, Q * b->k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    if (b->k && o->topk_score) CU(cudaMemcpyAsync(o->topk_score, b->topk_score.p, Q * b->k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (o->n_results) CU(cudaMemcpyAsync(o->n_results, b->n_results, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if (o->doc_digest) CU(cudaMemcpyAsync(o->doc_digest, b->doc_digest, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if (o->score_digest) CU(cudaMemcpyAsync(o->score_digest, b->score_digest, Q * sizeof(ull), cudaMemcpyDeviceToHost, st));
+    if (o->topk_n) CU(cudaMemcpyAsync(o->topk_n, b->topk_n, Q * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (b->k && o->topk_doc) CU(cudaMemcpyAsync(o->topk_doc, b->topk_doc, Q * b->k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (b->k && o->topk_score) CU(cudaMemcpyAsync(o->topk_score, b->topk_score, Q * b->k * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
   return PB_OK;
@@ -1146,12 +1250,95 @@ int pb_batch_fetch(pb_batch* b, pb_query_results* out) {
 
 void pb_batch_destroy(pb_batch* b) { delete b; }
 
+int pb_batch_reload(pb_batch* b, const pb_query_batch_desc* q) {
+  if (!b || !q) { pb::set_error("pb_batch_reload: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({ return batch_load(b, q, 0); });
+}
+
+int pb_batch_set_gather(pb_batch* b, pb_comm* comm, uint64_t slot_queries) {
+  if (!b) { pb::set_error("pb_batch_set_gather: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    if (comm && pbg::comm_device(comm) != b->ix->device) { pb::set_error("pb_batch_set_gather: the communicator lives on device %d, the batch on device %d", pbg::comm_device(comm), b->ix->device); return PB_ERR_INVALID; }
+    if (comm && slot_queries < b->Q) { pb::set_error("pb_batch_set_gather: slot of %llu queries is smaller than the batch (%llu)", (ull)slot_queries, (ull)b->Q); return PB_ERR_INVALID; }
+    CU(cudaSetDevice(b->ix->device));
+    CU(cudaStreamSynchronize(b->stream));
+    b->comm = comm;
+    b->want_slot = comm ? slot_queries : 0;
+    b->ran = false; b->gathered = false;
+    return batch_layout_results(b);
+  });
+}
+
+int pb_batch_run_local(pb_batch* b) {
+  if (!b) return PB_ERR_INVALID;
+  PB_TRY({
+    RC(batch_compute(b));
+    return batch_finish(b);
+  });
+}
+
+int pb_batch_gather(pb_batch* b) {
+  if (!b) return PB_ERR_INVALID;
+  if (!b->ran) { pb::set_error("pb_batch_gather: batch has not been run"); return PB_ERR_INVALID; }
+  PB_TRY({ return batch_gather(b); });
+}
+
+int pb_batch_sync(pb_batch* b) {
+  if (!b) return PB_ERR_INVALID;
+  PB_TRY({
+    CU(cudaSetDevice(b->ix->device));
+    CU(cudaStreamSynchronize(b->stream));
+    if (b->gather_pending) {
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, b->ev[6], b->ev[7]));
+      b->st.ms_gather = ms;
+      b->gathered = true;
+      b->gather_pending = false;
+    }
+    return PB_OK;
+  });
+}
+
+int pb_batch_fetch_gathered(pb_batch* b, uint64_t n_total, pb_query_results* o) {
+  if (!b || !o) return PB_ERR_INVALID;
+  PB_TRY({
+    RC(pb_batch_sync(b));
+    if (!b->comm || !b->gathered) { pb::set_error("pb_batch_fetch_gathered: no gathered results (pb_batch_set_gather + pb_batch_run)"); return PB_ERR_INVALID; }
+    const uint64_t world = (uint64_t)pbg::comm_world(b->comm), slot = b->slot;
+    if (n_total > world * slot) { pb::set_error("pb_batch_fetch_gathered: %llu queries asked, the gather holds %llu", (ull)n_total, (ull)(world * slot)); return PB_ERR_INVALID; }
+    const ResLayout L = res_layout(slot, b->k);
+    cudaStream_t st = b->stream;
+    const uint32_t k = b->k;
+    for (uint64_t r = 0; r < world; ++r) {
+      const uint64_t g0 = r * slot;
+      if (g0 >= n_total) break;
+      const uint64_t n = std::min<uint64_t>(slot, n_total - g0);
+      const uint8_t* blk = b->gath.p + r * b->block_bytes;
+      if (o->n_results) CU(cudaMemcpyAsync(o->n_results + g0, blk + L.n, n * 8, cudaMemcpyDeviceToHost, st));
+      if (o->doc_digest) CU(cudaMemcpyAsync(o->doc_digest + g0, blk + L.dd, n * 8, cudaMemcpyDeviceToHost, st));
+      if (o->score_digest) CU(cudaMemcpyAsync(o->score_digest + g0, blk + L.sd, n * 8, cudaMemcpyDeviceToHost, st));
+      if (o->topk_n) CU(cudaMemcpyAsync(o->topk_n + g0, blk + L.tn, n * 4, cudaMemcpyDeviceToHost, st));
+      if (k && o->topk_doc) CU(cudaMemcpyAsync(o->topk_doc + g0 * k, blk + L.td, n * k * 4, cudaMemcpyDeviceToHost, st));
+      if (k && o->topk_score) CU(cudaMemcpyAsync(o->topk_score + g0 * k, blk + L.ts, n * k * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return PB_OK;
+  });
+}
+
+int pb_batch_device_gathered(pb_batch* b, const void** block0, uint64_t* block_bytes, uint64_t* slot_queries) {
+  if (!b || !block0 || !block_bytes || !slot_queries) return PB_ERR_INVALID;
+  if (!b->comm || !b->gathered) { pb::set_error("pb_batch_device_gathered: no gathered results"); return PB_ERR_INVALID; }
+  *block0 = b->gath.p; *block_bytes = b->block_bytes; *slot_queries = b->slot;
+  return PB_OK;
+}
+
 int pb_batch_device_results(pb_batch* b, pb_query_results* o) {
   if (!b || !o) return PB_ERR_INVALID;
   if (!b->ran) { pb::set_error("pb_batch_device_results: batch has not been run"); return PB_ERR_INVALID; }
-  o->n_results = (uint64_t*)b->n_results.p; o->doc_digest = (uint64_t*)b->doc_digest.p;
-  o->score_digest = (uint64_t*)b->score_digest.p; o->topk_n = b->topk_n.p; o->topk_doc = b->topk_doc.p;
-  o->topk_score = b->topk_score.p;
+  o->n_results = (uint64_t*)b->n_results; o->doc_digest = (uint64_t*)b->doc_digest;
+  o->score_digest = (uint64_t*)b->score_digest; o->topk_n = b->topk_n; o->topk_doc = b->topk_doc;
+  o->topk_score = b->topk_score;
   return PB_OK;
 }
 

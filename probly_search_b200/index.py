@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Any, Callable, Hashable, List, Optional, Sequence
 
@@ -111,6 +112,7 @@ class Index:
         self._key_to_id: dict = {}
         self._id_to_key: list = []
         self._ord_to_id: Optional[np.ndarray] = None
+        self._batches = weakref.WeakSet()   # staged DeviceBatch objects: invalidated when the pb_index is recreated
 
     # -- on-disk image (the reference has no serialisation) -----------------------
     def save_image(self, path: str) -> None:
@@ -135,6 +137,7 @@ class Index:
         self._image_dirty, self._live_dirty = True, False
         self._key_to_id, self._id_to_key, self._ord_to_id = {}, [], None
         self._flat_keys = True
+        self._batches = weakref.WeakSet()
         return self
 
     # -- lifecycle ---------------------------------------------------------------------------
@@ -143,8 +146,7 @@ class Index:
             self._L.pb_image_file_free(self._image_file)
             self._image_file = None
         if getattr(self, "_ix", None):
-            self._L.pb_index_destroy(self._ix)
-            self._ix = None
+            self._drop_device_index()
         if getattr(self, "_b", None):
             self._L.pb_builder_destroy(self._b)
             self._b = None
@@ -234,8 +236,7 @@ class Index:
         im = self.flatten()
         if self._ix is None or self._image_dirty:
             if self._ix is not None:
-                self._L.pb_index_destroy(self._ix)
-                self._ix = None
+                self._drop_device_index()
             h = C.c_void_p()
             capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
             self._ix = h
@@ -250,6 +251,32 @@ class Index:
         self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
         self._image_dirty = False
         self._live_dirty = False
+
+    def set_live_state(self, removed_ordinals: np.ndarray, n_live_docs: int, field_avg: Sequence[float]) -> None:
+        """pb_index_set_live_state on the resident image: the FULL removed set, the live doc count and the
+        per-field averages of the pre-vacuum state (src/index.rs:161-191) — no re-flatten, no re-upload.
+        This is how an index served from an image file (no host builder) follows remove_document."""
+        self.sync_device()
+        ords = np.ascontiguousarray(removed_ordinals, dtype=np.uint32)
+        avg = (C.c_double * 4)(*(list(field_avg) + [0.0] * 4)[:4])
+        capi.check(self._L.pb_index_set_live_state(self._ix, ords.ctypes.data, len(ords), int(n_live_docs), avg))
+
+    def live_state(self):
+        """(removed ordinals, live doc count, field averages) of the host index, as set_live_state takes them."""
+        im = self.flatten()
+        nd = int(im.n_docs)
+        words = np.ctypeslib.as_array(im.removed_bitmap, shape=((nd + 31) // 32 + 1,))
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:nd]
+        ords = np.ascontiguousarray(np.nonzero(bits)[0], dtype=np.uint32)
+        return ords, int(im.n_live_docs), [float(im.field_avg[i]) for i in range(self.fields_num)]
+
+    def _drop_device_index(self) -> None:
+        """Destroys the pb_index; staged batches hold its raw handle, so they are closed first and any
+        later use of them raises instead of touching freed memory."""
+        for b in list(getattr(self, "_batches", ())):
+            b._invalidate()
+        self._L.pb_index_destroy(self._ix)
+        self._ix = None
 
     def _key_of_ord(self, o: int):
         kid = int(self._ord_to_id[o])
@@ -345,7 +372,8 @@ class Index:
 
 class DeviceBatch:
     """Staged form of a batch (pb_batch_create / run / fetch): upload once, run many times with
-    the inputs resident in HBM."""
+    the inputs resident in HBM.  With `set_gather(comm, slot)` every run ends with ONE
+    ncclAllGather of the packed result block on the batch's stream (multi-GPU)."""
 
     def __init__(self, index: Index, fq: FlatQueries, score_calculator, fields_boost: Sequence[float], top_k: int = 10):
         index.sync_device()
@@ -353,29 +381,68 @@ class DeviceBatch:
         self.index = index
         self.fq = fq
         self.top_k = top_k
+        self._calc = score_calculator
+        self._fields_boost = list(fields_boost)
         d, self._boosts = index._desc(fq, score_calculator, fields_boost, top_k)
         h = C.c_void_p()
         capi.check(self._L.pb_batch_create(index._ix, C.byref(d), C.byref(h)))
         self._h = h
+        self._stale = False
+        self._comm = None
+        index._batches.add(self)
+
+    def _handle(self):
+        if self._stale or not getattr(self, "_h", None):
+            raise capi.ProblyError(capi.PB_ERR_INVALID, "this DeviceBatch was staged on a device image that has since been "
+                                   "rebuilt (add_document / vacuum) or closed; stage a new one")
+        return self._h
+
+    def _invalidate(self) -> None:
+        self.close()
+        self._stale = True
+
+    def reload(self, fq: FlatQueries) -> None:
+        """Stages a new query batch into the same pb_batch (keeps stream, workspace and gather)."""
+        d, self._boosts = self.index._desc(fq, self._calc, self._fields_boost, self.top_k)
+        capi.check(self._L.pb_batch_reload(self._handle(), C.byref(d)))
+        self.fq = fq
+
+    def set_gather(self, comm, slot_queries: int) -> None:
+        capi.check(self._L.pb_batch_set_gather(self._handle(), comm._h if comm is not None else None, int(slot_queries)))
+        self._comm = comm
+        self._slot = int(slot_queries)
 
     def run(self) -> None:
-        capi.check(self._L.pb_batch_run(self._h))
+        capi.check(self._L.pb_batch_run(self._handle()))
+
+    def run_local(self) -> None:
+        capi.check(self._L.pb_batch_run_local(self._handle()))
 
     def fetch(self) -> BatchResults:
         res = BatchResults(self.fq.n_queries, self.top_k)
         rs = res.c_struct()
-        capi.check(self._L.pb_batch_fetch(self._h, C.byref(rs)))
+        capi.check(self._L.pb_batch_fetch(self._handle(), C.byref(rs)))
+        return res
+
+    def fetch_gathered(self, n_total: Optional[int] = None) -> BatchResults:
+        """Results of ALL ranks in global query order (rank r's query i = r * slot + i)."""
+        if self._comm is None:
+            raise capi.ProblyError(capi.PB_ERR_INVALID, "no gather attached")
+        n = int(n_total if n_total is not None else self._comm.world * self._slot)
+        res = BatchResults(n, self.top_k)
+        rs = res.c_struct()
+        capi.check(self._L.pb_batch_fetch_gathered(self._handle(), n, C.byref(rs)))
         return res
 
     def stats(self) -> dict:
         s = capi.BatchStats()
-        capi.check(self._L.pb_batch_get_stats(self._h, C.byref(s)))
+        capi.check(self._L.pb_batch_get_stats(self._handle(), C.byref(s)))
         return s.as_dict()
 
     def device_results(self) -> capi.QueryResults:
-        """Device pointers of the result buffers (for the NCCL top-k gather)."""
+        """Device pointers of the result buffers."""
         r = capi.QueryResults()
-        capi.check(self._L.pb_batch_device_results(self._h, C.byref(r)))
+        capi.check(self._L.pb_batch_device_results(self._handle(), C.byref(r)))
         return r
 
     def close(self) -> None:
