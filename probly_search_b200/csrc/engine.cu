@@ -119,6 +119,12 @@ struct pb_index {
   DBuf<uint2> dir;              // rank directories of the dense posting lists (IndexView::dir)
   DBuf<uint32_t> term_dir;
   uint32_t dir_words = 0, n_dense = 0;
+  // union image (union_kernels.cuh): the posting rows re-sorted by (doc shard, term, doc)
+  DBuf<uint32_t> u_meta, u_term, u_shard_row;
+  DBuf<uint16_t> u_code[4];
+  uint32_t u_wbits = 0, u_shards = 0;
+  bool u_ok = false;
+  DBuf<ull> liverowcnt_prefix, dflive_prefix;   // per-term prefixes of term_live_rows / term_df_live (class-U row statistics)
   // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
   std::vector<uint32_t> h_node_parent, h_node_char, h_term_node;
   std::vector<uint64_t> h_term_row_begin, h_df_live;
@@ -128,6 +134,13 @@ struct pb_index {
   std::mutex mu;                 // guards `scratch`
   pb_batch* scratch = nullptr;   // reused by pb_query_batch / pb_query_full / expand_term
 
+  UnionView uview() const {
+    UnionView u;
+    u.meta = u_meta.p; u.term = u_term.p;
+    for (int f = 0; f < 4; ++f) u.code[f] = u_code[f].p;
+    u.shard_row = u_shard_row.p; u.n_shards = u_shards; u.wbits = u_wbits; u.ok = u_ok ? 1u : 0u;
+    return u;
+  }
   IndexView view() const {
     IndexView v;
     v.node_edge_begin = node_edge_begin.p; v.node_term_lo = node_term_lo.p; v.node_term_hi = node_term_hi.p;
@@ -145,6 +158,52 @@ struct pb_index {
     return v;
   }
 };
+
+// Builds the union image on the device from the term-major image already resident in HBM: a stable
+// radix sort of (doc shard, row) keeps the rows of a shard in (term, doc) order.
+static int index_build_union(pb_index* ix) {
+  ix->u_ok = false;
+  const char* e = std::getenv("PB_UNION");
+  if (e && !std::strcmp(e, "0")) return PB_OK;
+  bool ok = ix->max_term_bytes <= 63u && ix->n_rows > 0 && ix->n_rows < 0xFFFFFF00ull && ix->n_terms > 0;
+  for (uint32_t f = 0; f < ix->F; ++f) {
+    ok = ok && ix->max_tf[f] <= 63u && ix->fl_bits[f] <= 8u;
+    ok = ok && (((uint64_t)ix->max_tf[f] + 1) << ix->fl_bits[f]) <= 65536ull;
+  }
+  if (!ok) return PB_OK;                      // outside the envelope of the dense path: queries take the per-list path
+  const uint64_t R = ix->n_rows, RP = R + 256;          // pad: 128-row groups are loaded whole
+  ix->u_wbits = 11;
+  if (const char* w = std::getenv("PB_UNION_WBITS")) ix->u_wbits = (uint32_t)std::min(12, std::max(7, atoi(w)));   // tuning knob
+  ix->u_shards = (uint32_t)(((ix->n_docs ? ix->n_docs - 1 : 0) >> ix->u_wbits) + 1);
+  DBuf<uint32_t> keys, vals, keys2, vals2, row_term;
+  DBuf<uint8_t> tmp;
+  CU(keys.ensure(R)); CU(vals.ensure(R)); CU(keys2.ensure(R)); CU(vals2.ensure(R)); CU(row_term.ensure(R));
+  IndexView v = ix->view();
+  ubuild_keys_kernel<<<ix->sm_count * 8, 256>>>(v, ix->u_wbits, keys.p, vals.p, row_term.p);
+  CU(cudaGetLastError());
+  const int end_bit = (int)bits_for((uint64_t)ix->u_shards + 1);
+  size_t bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, vals.p, vals2.p, (int64_t)R, 0, end_bit));
+  CU(tmp.ensure(bytes));
+  bytes = tmp.cap;
+  CU(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.p, keys2.p, vals.p, vals2.p, (int64_t)R, 0, end_bit));
+  CU(ix->u_meta.ensure(RP)); CU(ix->u_term.ensure(RP));
+  CU(cudaMemset(ix->u_meta.p, 0, ix->u_meta.cap * sizeof(uint32_t)));
+  CU(cudaMemset(ix->u_term.p, 0xFF, ix->u_term.cap * sizeof(uint32_t)));
+  for (uint32_t f = 0; f < ix->F; ++f) {
+    CU(ix->u_code[f].ensure(RP));
+    CU(cudaMemset(ix->u_code[f].p, 0, ix->u_code[f].cap * sizeof(uint16_t)));
+  }
+  ubuild_gather_kernel<<<(unsigned)((R + 255) / 256), 256>>>(v, ix->u_wbits, R, vals2.p, row_term.p, ix->u_meta.p, ix->u_term.p,
+                                                             ix->u_code[0].p, ix->u_code[1].p, ix->u_code[2].p, ix->u_code[3].p);
+  CU(cudaGetLastError());
+  CU(ix->u_shard_row.ensure(ix->u_shards + 2));
+  ubuild_bounds_kernel<<<(ix->u_shards + 1 + 255) / 256, 256>>>(keys2.p, R, ix->u_shards, ix->u_shard_row.p);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  ix->u_ok = true;
+  return PB_OK;
+}
 
 static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, uint64_t n_removed,
                                   uint64_t n_live, const double* avg) {
@@ -183,6 +242,15 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
     idf[t] = std::log(1.0 + ((double)diff + 0.5) / ((double)frequency + 0.5));
     lp[t + 1] = lp[t] + (df > 0 ? 1u : 0u);
     lrp[t + 1] = lrp[t] + (df > 0 ? (ix->h_term_row_begin[t + 1] - ix->h_term_row_begin[t]) : 0);
+  }
+  {
+    std::vector<uint32_t> h_live_rows(NT + 1, 0);
+    if (NT) CU(cudaMemcpy(h_live_rows.data(), ix->term_live_rows.p, NT * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<ull> lrc(NT + 2, 0), dfp(NT + 2, 0);
+    for (size_t t = 0; t < NT; ++t) { lrc[t + 1] = lrc[t] + h_live_rows[t]; dfp[t + 1] = dfp[t] + ix->h_df_live[t]; }
+    CU(ix->liverowcnt_prefix.ensure(NT + 2)); CU(ix->dflive_prefix.ensure(NT + 2));
+    CU(cudaMemcpy(ix->liverowcnt_prefix.p, lrc.data(), (NT + 1) * sizeof(ull), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix->dflive_prefix.p, dfp.data(), (NT + 1) * sizeof(ull), cudaMemcpyHostToDevice));
   }
   CU(cudaMemcpy(ix->term_idf.p, idf.data(), (NT + 1) * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ix->live_prefix.p, lp.data(), (NT + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -236,7 +304,10 @@ struct pb_batch {
   // partial lists + counters
   DBuf<uint32_t> part_head, part_next, part_n, part_doc, counters;   // counters: [0] part_count [1] rec_count [2] error
   DBuf<double> part_score;
-  DBuf<ull> stats;            // [2][ST_COUNT]: S phase, G phase
+  DBuf<ull> stats;            // [3][ST_COUNT]: S phase, G phase, U (union) phase
+  DBuf<UQuery> uq;
+  DBuf<ull> q_isu, q_uidx, q_isu2, q_uidx2, u_counter;
+  DBuf<uint32_t> u_list, u_list2;
   // side path
   DBuf<uint32_t> bitmap;
   size_t bitmap_zeroed = 0;
@@ -426,7 +497,9 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   RC(batch_layout_results(b));
   CU(b->part_head.ensure(Q + 1));
   CU(b->counters.ensure(8));
-  CU(b->stats.ensure(2 * ST_COUNT));
+  CU(b->stats.ensure(3 * ST_COUNT));
+  CU(b->uq.ensure(Q + 1)); CU(b->q_isu.ensure(Q + 2)); CU(b->q_uidx.ensure(Q + 2)); CU(b->u_list.ensure(Q + 1));
+  CU(b->q_isu2.ensure(Q + 2)); CU(b->q_uidx2.ensure(Q + 2)); CU(b->u_list2.ensure(Q + 1)); CU(b->u_counter.ensure(8));
   if (full_cap) {
     CU(b->full_q.ensure(full_cap)); CU(b->full_doc.ensure(full_cap)); CU(b->full_score.ensure(full_cap));
   }
@@ -547,7 +620,8 @@ int batch_compute(pb_batch* b) {
   CU(cudaMemsetAsync(b->res.p, 0, b->block_bytes, st));      // counts, digests, top-k: one packed block
   CU(cudaMemsetAsync(b->part_head.p, 0xFF, (Q + 1) * sizeof(uint32_t), st));
   CU(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(uint32_t), st));
-  CU(cudaMemsetAsync(b->stats.p, 0, 2 * ST_COUNT * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->stats.p, 0, 3 * ST_COUNT * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->u_counter.p, 0, 8 * sizeof(ull), st));
   CU(cudaMemsetAsync(b->q_prim.p, 0, (Q + 2) * sizeof(ull), st));
   CU(cudaMemsetAsync(b->full_count.p, 0, 2 * sizeof(ull), st));
   if (Q == 0) {
@@ -566,9 +640,22 @@ int batch_compute(pb_batch* b) {
   }
   CU(cudaEventRecord(b->ev[1], st));
   // ---- plan ------------------------------------------------------------------------------
+  UPlan up;
+  std::memset(&up, 0, sizeof(up));
+  up.enabled = (b->scorer == PB_SCORER_ZERO_TO_ONE && ix->u_ok) ? 1u : 0u;
+  {
+    uint64_t div = 16;
+    if (const char* e = std::getenv("PB_UNION_MIN_DIV")) div = (uint64_t)std::max<long long>(0, atoll(e));
+    up.min_rows = div ? ix->n_docs / div : 0;
+  }
+  up.uq = b->uq.p; up.q_isu = b->q_isu.p; up.q_isu2 = b->q_isu2.p;
+  up.allow_gen = union_smem_bytes((int)ix->F, ix->u_wbits, true) <= (226u << 10) ? 1u : 0u;
+  if (union_smem_bytes((int)ix->F, ix->u_wbits, false) > (226u << 10)) up.enabled = 0;
+  up.liverowcnt_prefix = ix->liverowcnt_prefix.p; up.dflive_prefix = ix->dflive_prefix.p;
+  up.stats = b->stats.p + 2 * ST_COUNT;
   plan_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(view, Q, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p,
                                                                  b->qt_len.p, b->seg_s.p, b->s_tiles.p, b->qt_gcount.p,
-                                                                 b->qt_q.p, b->q_isg.p, b->q_grows.p, b->stats.p);
+                                                                 b->qt_q.p, b->q_isg.p, b->q_grows.p, b->stats.p, up);
   CU(cudaGetLastError());
   ++launches;
   // the exclusive scans below run over n + 1 entries: give the extra input entry a defined value
@@ -577,6 +664,16 @@ int batch_compute(pb_batch* b) {
   RC(scan_ull(b, b->s_tiles.p, b->s_tile_off.p, Q + 1));
   RC(scan_ull(b, b->qt_gcount.p, b->qt_goff.p, NT + 1));
   launches += 2;
+  ull h_nu = 0, h_nu2 = 0;            // class-U queries: without / with overlapping term ranges
+  if (up.enabled) {
+    CU(cudaMemsetAsync(b->q_isu.p + Q, 0, sizeof(ull), st));
+    CU(cudaMemsetAsync(b->q_isu2.p + Q, 0, sizeof(ull), st));
+    RC(scan_ull(b, b->q_isu.p, b->q_uidx.p, Q + 1));
+    RC(scan_ull(b, b->q_isu2.p, b->q_uidx2.p, Q + 1));
+    launches += 2;
+    CU(cudaMemcpyAsync(&h_nu, b->q_uidx.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h_nu2, b->q_uidx2.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
+  }
   ull h_tot[2] = {0, 0};
   CU(cudaMemcpyAsync(&h_tot[0], b->s_tile_off.p + Q, sizeof(ull), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&h_tot[1], b->qt_goff.p + NT, sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -662,13 +759,15 @@ int batch_compute(pb_batch* b) {
   // partial top-k lists: <= 2 per warp per launch + 2 per class-G query
   const uint64_t max_warps = (uint64_t)ix->sm_count * 8 * WARPS_PER_CTA;
   const uint64_t n_gq = n_gsegs ? b->h_gidx[Q] : 0;
-  uint64_t part_cap = 2 * max_warps * (1 + 2 * rounds.size()) + 2 * n_gq + 64;
+  const uint64_t u_chunks = ix->u_ok ? (ix->u_shards + U_CHUNK - 1) / U_CHUNK : 0;
+  const uint64_t u_items = (h_nu + h_nu2) * u_chunks;
+  uint64_t part_cap = 2 * max_warps * (1 + 2 * rounds.size()) + 2 * n_gq + 64 + u_items;
   if (part_cap >= 0xFFFFFFF0ull) { pb::set_error("too many partial lists"); return PB_ERR_UNSUPPORTED; }
   const uint32_t kk = std::max<uint32_t>(k, 1);
   CU(b->part_next.ensure(part_cap)); CU(b->part_n.ensure(part_cap));
   CU(b->part_doc.ensure(part_cap * kk));
   CU(b->part_score.ensure(part_cap * kk));
-  uint64_t part_bound = 2 * max_warps;      // host-side upper bound of the device's partial-list counter
+  uint64_t part_bound = 2 * max_warps + u_items;      // host-side upper bound of the device's partial-list counter
 
   ScoreParams P;
   std::memset(&P, 0, sizeof(P));
@@ -706,6 +805,33 @@ int batch_compute(pb_batch* b) {
     S.score_launches = 1;
   }
   CU(cudaEventRecord(b->ev[3], st));
+
+  // ---- class U: union-heavy ZeroToOne queries, one dense pass (union_kernels.cuh) -----------
+  for (int gen = 0; gen < 2; ++gen) {
+    const ull nu = gen ? h_nu2 : h_nu;
+    if (!nu) continue;
+    const ull* isu = gen ? b->q_isu2.p : b->q_isu.p;
+    const ull* uidx = gen ? b->q_uidx2.p : b->q_uidx.p;
+    uint32_t* list = gen ? b->u_list2.p : b->u_list.p;
+    ucompact_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(Q, isu, uidx, list);
+    CU(cudaGetLastError());
+    UnionParams UP;
+    std::memset(&UP, 0, sizeof(UP));
+    UP.ix = view; UP.uv = ix->uview(); UP.out = P.out;
+    UP.uq = b->uq.p; UP.u_list = list; UP.n_u = (uint32_t)nu; UP.n_chunks = (uint32_t)u_chunks;
+    UP.item_counter = b->u_counter.p + gen;
+    UP.prof = b->u_counter.p + 2;
+    const size_t smem = union_smem_bytes((int)ix->F, ix->u_wbits, gen != 0);
+    int per_sm = 0;
+    CU(field_ops(ix->F)->union_occupancy(gen != 0, &per_sm, smem));
+    if (per_sm < 1) { pb::set_error("union kernel does not fit an SM (%zu B shared)", smem); return PB_ERR_CUDA; }
+    const int grid = (int)std::min<uint64_t>((uint64_t)ix->sm_count * per_sm, nu * u_chunks);
+    const int e0 = b->rev_begin();
+    CU(field_ops(ix->F)->union_launch(gen != 0, &UP, grid, smem, st));
+    b->rev_end(3, e0);
+    launches += 2;
+    S.union_queries += nu;
+  }
 
   // ---- class G: rounds of the side path --------------------------------------------------
   if (!rounds.empty()) {
@@ -886,7 +1012,7 @@ int batch_finish(pb_batch* b) {
   cudaStream_t st = b->stream;
   pb_batch_stats& S = b->st;
   CU(cudaSetDevice(ix->device));
-  ull h_stats[2 * ST_COUNT];
+  ull h_stats[3 * ST_COUNT];
   uint32_t h_cnt[4] = {0, 0, 0, 0};
   ull h_full[2] = {0, 0};
   CU(cudaMemcpyAsync(h_full, b->full_count.p, sizeof(h_full), cudaMemcpyDeviceToHost, st));
@@ -898,9 +1024,10 @@ int batch_finish(pb_batch* b) {
   if (h_cnt[2] & 2u) { pb::set_error("internal: side-path record buffer overflow"); return PB_ERR_INVALID; }
   if (h_cnt[2] & 8u) { pb::set_error("a query expands to more than 2^27 posting lists"); return PB_ERR_UNSUPPORTED; }
   if (h_cnt[2] & 4u) { pb::set_error("a document received more than 64 (query term, expansion) events in one ZeroToOne query"); return PB_ERR_UNSUPPORTED; }
-  S.rows_streamed = h_stats[ST_ROWS_STREAMED] + h_stats[ST_COUNT + ST_ROWS_STREAMED];
-  S.rows_scored = h_stats[ST_ROWS_SCORED] + h_stats[ST_COUNT + ST_ROWS_SCORED];
-  S.pointer_visits = h_stats[ST_POINTER_VISITS] + h_stats[ST_COUNT + ST_POINTER_VISITS];
+  S.rows_streamed = h_stats[ST_ROWS_STREAMED] + h_stats[ST_COUNT + ST_ROWS_STREAMED] + h_stats[2 * ST_COUNT + ST_ROWS_STREAMED];
+  S.rows_scored = h_stats[ST_ROWS_SCORED] + h_stats[ST_COUNT + ST_ROWS_SCORED] + h_stats[2 * ST_COUNT + ST_ROWS_SCORED];
+  S.pointer_visits = h_stats[ST_POINTER_VISITS] + h_stats[ST_COUNT + ST_POINTER_VISITS] + h_stats[2 * ST_COUNT + ST_POINTER_VISITS];
+  S.rows_streamed_union = h_stats[2 * ST_COUNT + ST_ROWS_STREAMED];
   S.rows_diverted = h_stats[ST_COUNT + ST_ROWS_DIVERTED];
   S.rows_streamed_direct = h_stats[ST_ROWS_STREAMED];
   S.results_emitted = h_full[1];
@@ -921,6 +1048,12 @@ int batch_finish(pb_batch* b) {
     }
   }
   S.rows_streamed_side = h_stats[ST_COUNT + ST_ROWS_STREAMED];
+  if (std::getenv("PB_UNION_PROF") && S.union_queries) {
+    ull h_prof[6] = {0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpy(h_prof, b->u_counter.p + 2, sizeof(h_prof), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[pb] union kernel cycles (thread 0 of every CTA): setup %llu count %llu score %llu merge-docs %llu item-end %llu, items %llu\n",
+            h_prof[0], h_prof[1], h_prof[2], h_prof[5], h_prof[3], h_prof[4]);
+  }
   S.ms_gather = 0.f;
   if (b->gather_pending) {
     CU(cudaEventElapsedTime(&ms, b->ev[6], b->ev[7])); S.ms_gather = ms;
@@ -1048,6 +1181,7 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
         CU(upload(ix->post_blocks, nb.data(), nb.size(), 0));
       }
     }
+    RC(index_build_union(ix));
     // rank directories of the dense lists (>= n_docs / 32 rows, capped at 1 GB): built on the device
     {
       std::vector<uint32_t> tdir(im->n_terms + 1, 0u), dense;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
+#include "union_kernels.cuh"
 
 namespace pbk {
 
@@ -17,6 +18,8 @@ struct FieldOps {
   cudaError_t (*binfold_launch)(int scorer, const ScoreParams* P, int grid, cudaStream_t st);
   cudaError_t (*live_df_launch)(const IndexView* ix, unsigned long long* df_live, uint32_t* live_rows, int grid,
                                 cudaStream_t st);
+  cudaError_t (*union_occupancy)(bool gen, int* per_sm, size_t smem);
+  cudaError_t (*union_launch)(bool gen, const UnionParams* P, int grid, size_t smem, cudaStream_t st);
 };
 
 const FieldOps* field_ops_f1();

@@ -349,11 +349,23 @@ struct WarpAcc {
   // Four rows per lane at once (the scoring kernel's tile shape).  `some` = 4-bit mask of rows
   // that produced a result.  The top-k structure is only touched when some lane holds a score
   // that reaches the current k-th best.
-  template <bool CAPTURE>
+  // TIES: scores that tie with the k-th best are common (ZeroToOne): the pre-test is the exact comparison, so a
+  // tie with a larger doc ordinal does not enter the insertion loop.
+  template <bool CAPTURE, bool TIES = false>
   __device__ __forceinline__ void add4(const Outputs& o, uint32_t some, const uint32_t (&doc)[4],
                                        const double (&sc)[4], int lane) {
     bool hit = false;
-    if (__all_sync(0xffffffffu, some == 0xFu)) {            // the common case: every row produced a result
+    if (TIES) {
+      cnt += __popc(some);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = 0u - ((some >> j) & 1u);
+        const uint32_t a = doc_mix(doc[j]);
+        dd += sq64(a & m);
+        sd += sq64(score_mix(a, sc[j]) & m);
+        hit |= (m != 0u) && better(sc[j], doc[j], thr_s, thr_d);
+      }
+    } else if (__all_sync(0xffffffffu, some == 0xFu)) {            // the common case: every row produced a result
       cnt += 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

@@ -62,7 +62,23 @@ cudaError_t live_df_launch(const IndexView* ix, unsigned long long* df_live, uin
   return cudaGetLastError();
 }
 
-const FieldOps OPS = {score_occupancy, score_launch, mark_launch, fold_launch, binfold_launch, live_df_launch};
+template <bool GEN>
+cudaError_t union_occ_t(int* per_sm, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(union_kernel<F, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, union_kernel<F, GEN>, UShape<GEN>::THREADS, smem);
+}
+cudaError_t union_occupancy(bool gen, int* per_sm, size_t smem) {
+  return gen ? union_occ_t<true>(per_sm, smem) : union_occ_t<false>(per_sm, smem);
+}
+cudaError_t union_launch(bool gen, const UnionParams* P, int grid, size_t smem, cudaStream_t st) {
+  if (gen) union_kernel<F, true><<<grid, UShape<true>::THREADS, smem, st>>>(*P);
+  else union_kernel<F, false><<<grid, UShape<false>::THREADS, smem, st>>>(*P);
+  return cudaGetLastError();
+}
+
+const FieldOps OPS = {score_occupancy, score_launch, mark_launch, fold_launch, binfold_launch, live_df_launch,
+                      union_occupancy, union_launch};
 
 }  // namespace
 

@@ -3,6 +3,7 @@
 // per-field-count kernels live in kernels.cuh and are compiled once per F in kernels_f.cu.
 #pragma once
 #include "kernels.cuh"
+#include "union_kernels.cuh"
 
 namespace pbk {
 // ------------------------------------------------------------------------------------------
@@ -100,6 +101,19 @@ __device__ __forceinline__ uint32_t first_live_term(const IndexView& ix, uint32_
   return a;
 }
 
+// What plan_query_kernel needs to route a query to the dense union path.
+struct UPlan {
+  uint32_t enabled;
+  uint32_t allow_gen;                          // the two-candidate kernel fits shared memory at this field count
+  unsigned long long min_rows;                 // a class-U query streams at least this many rows
+  UQuery* uq;                                  // [n_queries]
+  unsigned long long* q_isu;                   // [n_queries + 1] class U without overlapping term ranges
+  unsigned long long* q_isu2;                  // [n_queries + 1] class U with overlaps (general kernel)
+  const unsigned long long* liverowcnt_prefix; // [n_terms + 1] rows whose doc is live, before term t
+  const unsigned long long* dflive_prefix;     // [n_terms + 1] live occurrence counts before term t
+  unsigned long long* stats;                   // [ST_COUNT] of the union launch
+};
+
 // One thread per query.  Classifies the query by the number of live posting lists its terms
 // expand to (terms whose live df is 0 are skipped, query.rs:48):
 //   0 lists  -> empty result          1 list -> class S: one DIRECT segment (seg_s[q])
@@ -110,9 +124,11 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
                                   const uint32_t* __restrict__ qt_len, Seg* __restrict__ seg_s,
                                   unsigned long long* __restrict__ s_tiles, unsigned long long* __restrict__ qt_gcount,
                                   uint32_t* __restrict__ qt_q, unsigned long long* __restrict__ q_isg,
-                                  unsigned long long* __restrict__ q_grows, unsigned long long* __restrict__ stats) {
+                                  unsigned long long* __restrict__ q_grows, unsigned long long* __restrict__ stats,
+                                  UPlan up) {
   uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   unsigned long long st_rows = 0, st_live = 0, st_ptr = 0;
+  unsigned long long su_rows = 0, su_live = 0, su_ptr = 0;
   if (q < n_queries) {
   uint64_t t0 = query_term_off[q], t1 = query_term_off[q + 1];
   uint32_t nl = 0;
@@ -144,6 +160,42 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
   seg_s[q] = s;
   s_tiles[q] = tiles;
   bool g = nl >= 2;
+  // class U (union_kernels.cuh): ZeroToOne, several lists, a large part of the corpus, few enough
+  // query terms / overlaps for the dense per-doc state
+  bool u = false, ugen = false;
+  if (up.enabled && g && rows >= up.min_rows && t1 - t0 <= 255) {
+    UQuery d;
+    d.q = (uint32_t)q; d.qtl = (uint32_t)(t1 - t0); d.n_act = 0; d.overlaps = 0;
+    bool ok = true;
+    for (uint64_t t = t0; t < t1 && ok; ++t) {
+      const uint32_t lo = qt_lo[t], hi = qt_hi[t];
+      if (ix.live_prefix[hi] == ix.live_prefix[lo]) continue;
+      if (d.n_act == (uint32_t)U_MAX_ACT || hi - lo > (1u << 20) || qt_len[t] > 63u) { ok = false; break; }
+      d.lo[d.n_act] = lo; d.hi[d.n_act] = hi; d.qti[d.n_act] = (uint8_t)(t - t0); d.qlen[d.n_act] = (uint8_t)qt_len[t];
+      ++d.n_act;
+    }
+    for (uint32_t a = d.n_act; a < (uint32_t)U_MAX_ACT; ++a) { d.lo[a] = 0; d.hi[a] = 0; d.qti[a] = 0; d.qlen[a] = 0; }
+    for (uint32_t a = 0; a < (uint32_t)U_MAX_ACT; ++a) {
+      uint32_t dep = a < d.n_act ? 1u : 0u;          // + one candidate per other query term whose range overlaps
+      for (uint32_t b2 = 0; b2 < d.n_act && a < d.n_act; ++b2)
+        if (b2 != a && d.lo[a] < d.hi[b2] && d.lo[b2] < d.hi[a]) ++dep;
+      d.depth[a] = (uint8_t)dep; d.pad[a] = 0;
+      if (dep > 1) d.overlaps = 1;
+      ok = ok && dep <= (up.allow_gen ? 2u : 1u);    // the general kernel keeps two candidates per query term
+    }
+    if (ok) {
+      u = true;
+      ugen = d.overlaps != 0;
+      g = false;
+      up.uq[q] = d;
+      for (uint32_t a = 0; a < d.n_act; ++a) {
+        su_rows += ix.term_row_begin[d.hi[a]] - ix.term_row_begin[d.lo[a]];      // the union image streams every row of the range
+        su_live += up.liverowcnt_prefix[d.hi[a]] - up.liverowcnt_prefix[d.lo[a]];
+        su_ptr += up.dflive_prefix[d.hi[a]] - up.dflive_prefix[d.lo[a]];
+      }
+    }
+  }
+  if (up.q_isu) { up.q_isu[q] = (u && !ugen) ? 1ull : 0ull; up.q_isu2[q] = (u && ugen) ? 1ull : 0ull; }
   q_isg[q] = g ? 1ull : 0ull;
   q_grows[q] = g ? rows : 0ull;
   for (uint64_t t = t0; t < t1; ++t)
@@ -155,6 +207,63 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
     atomicAdd(&stats[ST_ROWS_SCORED], st_live);
     atomicAdd(&stats[ST_POINTER_VISITS], st_ptr);
   }
+  su_rows = warp_sum_u64(su_rows); su_live = warp_sum_u64(su_live); su_ptr = warp_sum_u64(su_ptr);
+  if ((threadIdx.x & 31) == 0 && su_rows) {
+    atomicAdd(&up.stats[ST_ROWS_STREAMED], su_rows);
+    atomicAdd(&up.stats[ST_ROWS_SCORED], su_live);
+    atomicAdd(&up.stats[ST_POINTER_VISITS], su_ptr);
+  }
+}
+
+// class-U query indices, compacted in query order (q_uidx = exclusive prefix of q_isu)
+__global__ void ucompact_kernel(uint64_t n_queries, const unsigned long long* __restrict__ q_isu,
+                                const unsigned long long* __restrict__ q_uidx, uint32_t* __restrict__ u_list) {
+  uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (q < n_queries && q_isu[q]) u_list[q_uidx[q]] = (uint32_t)q;
+}
+
+// ---- union image build (pb_index_create): rows re-sorted by (doc shard, term, doc) --------------------
+// pass 1: one warp per term writes, for each of its rows, the sort key (shard) and remembers the term
+__global__ void ubuild_keys_kernel(IndexView ix, uint32_t wbits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                   uint32_t* __restrict__ row_term) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = warp; t < ix.n_terms; t += nwarps) {
+    const uint64_t a = ix.term_row_begin[t], b = ix.term_row_begin[t + 1];
+    for (uint64_t r = a + lane; r < b; r += 32) {
+      keys[r] = row_doc(ix, r) >> wbits;
+      vals[r] = (uint32_t)r;
+      row_term[r] = (uint32_t)t;
+    }
+  }
+}
+// pass 2 (after a stable radix sort of (shard, row)): gather the rows into the union columns
+__global__ void ubuild_gather_kernel(IndexView ix, uint32_t wbits, uint64_t n_rows, const uint32_t* __restrict__ sorted_row,
+                                     const uint32_t* __restrict__ row_term, uint32_t* __restrict__ u_meta,
+                                     uint32_t* __restrict__ u_term, uint16_t* __restrict__ c0, uint16_t* __restrict__ c1,
+                                     uint16_t* __restrict__ c2, uint16_t* __restrict__ c3) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const uint64_t r = sorted_row[i];
+  const uint32_t t = row_term[r], doc = row_doc(ix, r);
+  u_meta[i] = (doc & ((1u << wbits) - 1u)) | (ix.term_byte_len[t] << 16);
+  u_term[i] = t;
+  uint16_t* cs[4] = {c0, c1, c2, c3};
+  for (uint32_t f = 0; f < ix.num_fields; ++f)
+    cs[f][i] = (uint16_t)((row_col(ix, r, (int)f) << ix.fl_bits[f]) | row_col(ix, r, (int)(ix.num_fields + f)));
+}
+// first row of every shard in the sorted key array (keys ascend)
+__global__ void ubuild_bounds_kernel(const uint32_t* __restrict__ sorted_keys, uint64_t n_rows, uint32_t n_shards,
+                                     uint32_t* __restrict__ shard_row) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n_shards) return;
+  uint64_t lo = 0, hi = n_rows;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (sorted_keys[mid] < s) lo = mid + 1; else hi = mid;
+  }
+  shard_row[s] = (uint32_t)lo;
 }
 
 // One warp per query term of a class-G query: writes one SECONDARY segment per live expanded

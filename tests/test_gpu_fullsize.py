@@ -70,19 +70,42 @@ def test_cfg1_full_size(corpus):
     assert int(im.n_rows) == 25_849_058 and int(im.n_terms) == 262_135   # the corpus is the one DESIGN.md describes
 
 
+def _golden(name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"fullsize_{name}.npz"))
+    return {k: g[k] for k in g.files}
+
+
 def test_cfg2_prefix_zero_to_one_full_corpus(corpus):
+    """BASELINE cfg 2 at full size: 400 leading queries against the committed oracle answers
+    (scripts/make_fullsize_goldens.py), the rest of a 3000-query batch through batch properties."""
     cfg, wl, ix, o = corpus
     k = 10
-    fq = wl.queries(300, mode=1)
+    g = _golden("cfg2")
+    assert int(g["n_docs"]) == cfg.n_docs and int(g["vocab"]) == cfg.vocab
+    fq = wl.queries(3000, mode=1)
     b = DeviceBatch(ix, fq, score.zero_to_one.new(), cfg.boosts, top_k=k)
     b.run()
     got, st = b.fetch(), b.stats()
-    _batch_properties(got, st, k)
-    n_check = 12
-    sub = fq.slice(0, n_check)
-    exp = o.query_batch_flat(sub.query_term_off, sub.term_bytes, sub.term_byte_off, orc.ZERO_TO_ONE, cfg.boosts, k,
-                             n_threads=8)
-    _check_against_oracle(got, exp, n_check)
+    c1 = _batch_properties(got, st, k)
+    _check_against_oracle(got, g, int(g["n_queries"]))
+    assert st["union_queries"] > 1500                                    # the dense union route carries this config
+    b.run()
+    assert _batch_properties(b.fetch(), b.stats(), k) == c1              # idempotent
+    # a fresh oracle run on a few queries guards the golden file itself
+    sub = fq.slice(0, 6)
+    exp = o.query_batch_flat(sub.query_term_off, sub.term_bytes, sub.term_byte_off, orc.ZERO_TO_ONE, cfg.boosts, k, n_threads=8)
+    _check_against_oracle(got, exp, 6)
+
+
+def test_cfg1_leading_queries_against_committed_goldens(corpus):
+    cfg, wl, ix, o = corpus
+    g = _golden("cfg1")
+    n = int(g["n_queries"])
+    fq = wl.queries(n)
+    b = DeviceBatch(ix, fq, score.bm25.new(), cfg.boosts, top_k=10)
+    b.run()
+    _check_against_oracle(b.fetch(), g, n)
 
 
 def test_cfg4_style_removed_and_boosts_full_corpus(corpus):
