@@ -363,7 +363,10 @@ struct WarpAcc {
         const uint32_t a = doc_mix(doc[j]);
         dd += sq64(a & m);
         sd += sq64(score_mix(a, sc[j]) & m);
-        hit |= (m != 0u) && better(sc[j], doc[j], thr_s, thr_d);
+        // scores here are >= +0.0 and the threshold is -1.0 or such a score: doubles of one sign order like their
+        // bit patterns read as signed integers, so the exact (score desc, doc asc) test needs no f64 compare
+        const long long sb = __double_as_longlong(sc[j]), tb = __double_as_longlong(thr_s);
+        hit |= (m != 0u) && (sb > tb || (sb == tb && doc[j] < thr_d));
       }
     } else if (__all_sync(0xffffffffu, some == 0xFu)) {            // the common case: every row produced a result
       cnt += 4;

@@ -50,7 +50,7 @@ constexpr int U_DE = 10, U_TF = 16;  // table of (s / tf) * tf by (explen - qlen
 constexpr int U_CHUNK = PB_U_CHUNK;  // shards per work item
 constexpr uint32_t U_SENT = 0xFFFFFFFFu;
 #ifndef PB_U_THREADS
-#define PB_U_THREADS 384
+#define PB_U_THREADS 256
 #endif
 #ifndef PB_U_MINBLOCKS
 #define PB_U_MINBLOCKS 2
@@ -90,10 +90,32 @@ struct UnionParams {
 
 __host__ __device__ inline size_t union_smem_bytes(int F, uint32_t wbits, bool gen) {
   const size_t W = (size_t)1 << wbits;
-  return (size_t)F * W * 16 * (gen ? 2 : 1) + (size_t)F * W + (size_t)W * 4    // candidate records, field lengths, event counters
+  return (size_t)F * W * 16 * (gen ? 2 : 1) + (size_t)F * W + (size_t)W * 8    // candidate records, field lengths, event counters x2
          + (size_t)U_MAX_ACT * U_DE * U_TF * 8 + (size_t)U_MAX_ACT * U_DE * 8  // v table, s table
          + 256 * 16                                                            // {m, RN(1/m)}
-         + (size_t)U_CHUNK * U_MAX_ACT * 2 * 4 + (size_t)W * 2 + 16;           // run bounds, multi-event doc list
+         + (size_t)U_CHUNK * U_MAX_ACT * 2 * 4 + (size_t)W * 4 + 16;           // run bounds, multi-event doc lists x2
+}
+
+// The rows of a shard are read twice (count pass, score pass) a few microseconds apart: these loads ALLOCATE in L1
+// (the single-list kernel streams with L1::no_allocate), and the lines of the next pass / next shard are prefetched.
+__device__ __forceinline__ uint4 ldg_keep(const uint32_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_keep_u64(const uint32_t* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// one 128-row group of the union image = 4 lines of meta, 4 of term, 2 per code column: lane l prefetches line l
+template <int F>
+__device__ __forceinline__ void prefetch_group(const UnionView& uv, uint32_t grp, int lane, bool with_meta) {
+  const uint32_t base = grp << 7;
+  if (with_meta && lane < 4) prefetch_l1(uv.meta + base + lane * 32);
+  else if (lane >= 4 && lane < 8) prefetch_l1(uv.term + base + (lane - 4) * 32);
+  else if (lane >= 8 && lane < 8 + 2 * F) prefetch_l1(uv.code[(lane - 8) >> 1] + base + ((lane - 8) & 1) * 64);
 }
 
 __device__ __forceinline__ uint32_t u4get(const uint4& v, int a) { return a == 0 ? v.x : a == 1 ? v.y : a == 2 ? v.z : v.w; }
@@ -166,8 +188,8 @@ union_kernel(const __grid_constant__ UnionParams P) {
   const uint32_t W = 1u << P.uv.wbits;
   uint4* top = reinterpret_cast<uint4*>(u_smem);                                  // [F][W]: best key per query term
   uint4* sec = top + (GEN ? (size_t)F * W : 0);                                   // [F][W]: second best (GEN)
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(top + (size_t)F * W * (GEN ? 2 : 1)); // [W] events per doc
-  double2* mrc = reinterpret_cast<double2*>(cnt + W);                             // [256] {m, RN(1 / m)}
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(top + (size_t)F * W * (GEN ? 2 : 1)); // [2][W] events per doc (two shards in flight)
+  double2* mrc = reinterpret_cast<double2*>(cnt + 2 * W);                         // [256] {m, RN(1 / m)}
   double* vt = reinterpret_cast<double*>(mrc + 256);                              // [act][U_DE][U_TF] (s / tf) * tf
   double* stab = vt + U_MAX_ACT * U_DE * U_TF;                                    // [act][U_DE] s
   uint32_t* bnd = reinterpret_cast<uint32_t*>(stab + U_MAX_ACT * U_DE);           // [U_CHUNK][act][2]
@@ -177,7 +199,7 @@ union_kernel(const __grid_constant__ UnionParams P) {
   __shared__ unsigned long long red_dd[NW], red_sd[NW];
   __shared__ uint32_t red_cnt[NW];
   __shared__ uint32_t n_multi[2];           // docs of the current shard with several events (two counters, alternating) ...
-  uint16_t* mlist = reinterpret_cast<uint16_t*>(flv + (size_t)F * W);   // ... and their list [W]
+  uint16_t* mlist = reinterpret_cast<uint16_t*>(flv + (size_t)F * W);   // ... and their lists [2][W]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long n_items = (unsigned long long)P.n_u * P.n_chunks;
@@ -185,9 +207,8 @@ union_kernel(const __grid_constant__ UnionParams P) {
   const bool capture = P.out.full_q != nullptr;
 
   for (uint32_t i = tid; i < 256; i += THREADS) mrc[i] = make_double2((double)i, __ldg(&P.ix.rcp[i]));
-  for (uint32_t i = tid; i < W; i += THREADS) cnt[i] = 0u;
+  for (uint32_t i = tid; i < 2 * W; i += THREADS) cnt[i] = 0u;
   if (tid == 0) { n_multi[0] = 0u; n_multi[1] = 0u; }
-  uint32_t par = 0;
 #if PB_UNION_PROF
   long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
 #define PB_UPROF(i) do { if (tid == 0) { const long long n_ = clock64(); pc[i] += n_ - pt; pt = n_; } } while (0)
@@ -226,6 +247,7 @@ union_kernel(const __grid_constant__ UnionParams P) {
       vt[i] = tf ? __dmul_rn(fmin(__ddiv_rn(s, (double)tf), 1.0), (double)tf) : 0.0;   // zero_to_one.rs:117-118
     }
     for (uint32_t i = tid; i < (uint32_t)F * W * (GEN ? 2u : 1u); i += THREADS) top[i] = SENT4;
+    if (tid == 0) { n_multi[0] = 0u; n_multi[1] = 0u; }
     WarpAcc acc;
     acc.reset(uq.q);
     __syncthreads();
@@ -234,32 +256,43 @@ union_kernel(const __grid_constant__ UnionParams P) {
     if (tid == 0) ++pc[4];
 #endif
 
-    for (uint32_t sh = s0; sh < s1; ++sh) {
+    // The shards of the item run as a two-barrier software pipeline:
+    //   [score(s)]  barrier  [merge(s) and count(next shard) side by side]  barrier  [score(next)] ...
+    // count(next) only touches the OTHER event-counter / list buffer, so it shares a barrier interval with merge(s).
+    struct Geo { uint32_t o1, o2, o3, total, ga, gb, gc, gd; };
+    auto geo_of = [&](uint32_t sh) {
       const uint32_t* b = bnd + (sh - s0) * U_MAX_ACT * 2;
-      // flattened space of 128-row groups over the runs of the shard
-      uint32_t o1, o2, o3, total, ga, gb, gc, gd;
-      {
-        uint32_t n[U_MAX_ACT], g[U_MAX_ACT];
+      uint32_t n[U_MAX_ACT], g[U_MAX_ACT];
 #pragma unroll
-        for (int a = 0; a < U_MAX_ACT; ++a) {
-          n[a] = 0; g[a] = 0;
-          if (a < (int)n_act && b[a * 2 + 1] > b[a * 2]) { g[a] = b[a * 2] >> 7; n[a] = ((b[a * 2 + 1] + 127u) >> 7) - g[a]; }
-        }
-        o1 = n[0]; o2 = o1 + n[1]; o3 = o2 + n[2]; total = o3 + n[3];
-        ga = g[0]; gb = g[1]; gc = g[2]; gd = g[3];
+      for (int a = 0; a < U_MAX_ACT; ++a) {
+        n[a] = 0; g[a] = 0;
+        if (a < (int)n_act && b[a * 2 + 1] > b[a * 2]) { g[a] = b[a * 2] >> 7; n[a] = ((b[a * 2 + 1] + 127u) >> 7) - g[a]; }
       }
-      if (total == 0) continue;                          // CTA-uniform: the query has no row in this shard
-      const uint32_t doc_base = sh << P.uv.wbits;
-      par ^= 1u;
-      if (tid == 0) n_multi[par ^ 1u] = 0u;               // the previous shard's counter: every warp is past its last read
+      Geo G;
+      G.o1 = n[0]; G.o2 = G.o1 + n[1]; G.o3 = G.o2 + n[2]; G.total = G.o3 + n[3];
+      G.ga = g[0]; G.gb = g[1]; G.gc = g[2]; G.gd = g[3];
+      return G;
+    };
+    auto next_shard = [&](uint32_t from, Geo& G) {        // first shard >= from in which the query has rows (CTA-uniform)
+      for (uint32_t sh = from; sh < s1; ++sh) {
+        G = geo_of(sh);
+        if (G.total) return sh;
+      }
+      return s1;
+    };
 
-      // ---- pass A: events per doc ---------------------------------------------------------------------
-      for (uint32_t t = warp; t < total; t += NW) {
-        const int a = (t >= o1 ? 1 : 0) + (t >= o2 ? 1 : 0) + (t >= o3 ? 1 : 0);
-        const uint32_t grp = a == 0 ? ga + t : a == 1 ? gb + (t - o1) : a == 2 ? gc + (t - o2) : gd + (t - o3);
+    // ---- pass A: events per doc ---------------------------------------------------------------------
+    auto pass_count = [&](uint32_t sh, const Geo& G, uint32_t buf) {
+      const uint32_t* b = bnd + (sh - s0) * U_MAX_ACT * 2;
+      uint32_t* cn = cnt + buf * W;
+      uint16_t* ml = mlist + buf * W;
+      const uint32_t doc_base = sh << P.uv.wbits;
+      for (uint32_t t = warp; t < G.total; t += NW) {
+        const int a = (t >= G.o1 ? 1 : 0) + (t >= G.o2 ? 1 : 0) + (t >= G.o3 ? 1 : 0);
+        const uint32_t grp = a == 0 ? G.ga + t : a == 1 ? G.gb + (t - G.o1) : a == 2 ? G.gc + (t - G.o2) : G.gd + (t - G.o3);
         const uint32_t r0 = b[a * 2], r1 = b[a * 2 + 1];
         const uint32_t base = (grp << 7) + lane * 4;
-        const uint4 m4 = ldg_stream(P.uv.meta + base);
+        const uint4 m4 = ldg_keep(P.uv.meta + base);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t r = base + j;
@@ -269,23 +302,26 @@ union_kernel(const __grid_constant__ UnionParams P) {
             const uint32_t d = doc_base + dl;
             if ((__ldg(&P.ix.removed[d >> 5]) >> (d & 31)) & 1u) continue;
           }
-          if (atomicAdd(&cnt[dl], 1u) == 1u) mlist[atomicAdd(&n_multi[par], 1u)] = (uint16_t)dl;   // second event: the doc needs the merge
+          if (atomicAdd(&cn[dl], 1u) == 1u) ml[atomicAdd(&n_multi[buf], 1u)] = (uint16_t)dl;   // second event: the doc needs the merge
         }
       }
-      __syncthreads();
-      PB_UPROF(1);
+    };
 
-      // ---- pass B: score the single-event docs inline, feed the dense state with the rest -------------
-      for (uint32_t t = warp; t < total; t += NW) {
-        const int a = (t >= o1 ? 1 : 0) + (t >= o2 ? 1 : 0) + (t >= o3 ? 1 : 0);
-        const uint32_t grp = a == 0 ? ga + t : a == 1 ? gb + (t - o1) : a == 2 ? gc + (t - o2) : gd + (t - o3);
+    // ---- pass B: score the single-event docs inline, feed the dense state with the rest -------------
+    auto pass_score = [&](uint32_t sh, const Geo& G, uint32_t buf) {
+      const uint32_t* b = bnd + (sh - s0) * U_MAX_ACT * 2;
+      uint32_t* cn = cnt + buf * W;
+      const uint32_t doc_base = sh << P.uv.wbits;
+      for (uint32_t t = warp; t < G.total; t += NW) {
+        const int a = (t >= G.o1 ? 1 : 0) + (t >= G.o2 ? 1 : 0) + (t >= G.o3 ? 1 : 0);
+        const uint32_t grp = a == 0 ? G.ga + t : a == 1 ? G.gb + (t - G.o1) : a == 2 ? G.gc + (t - G.o2) : G.gd + (t - G.o3);
         const uint32_t r0 = b[a * 2], r1 = b[a * 2 + 1];
         const uint32_t base = (grp << 7) + lane * 4;
-        const uint4 m4 = ldg_stream(P.uv.meta + base);
-        const uint4 t4 = ldg_stream(P.uv.term + base);
+        const uint4 m4 = ldg_keep(P.uv.meta + base);
+        const uint4 t4 = ldg_keep(P.uv.term + base);
         uint2 c4[F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) c4[f] = ldg_stream_u64(reinterpret_cast<const uint32_t*>(P.uv.code[f] + base));
+        for (int f = 0; f < F; ++f) c4[f] = ldg_keep_u64(reinterpret_cast<const uint32_t*>(P.uv.code[f] + base));
         const uint32_t lo_a = uq.lo[a], ql = uq.qlen[a];
         const bool two = GEN && uq.depth[a] > 1;
         const double* vta = vt + a * (U_DE * U_TF);
@@ -297,11 +333,11 @@ union_kernel(const __grid_constant__ UnionParams P) {
           const uint32_t r = base + j;
           const uint32_t meta = u4c(m4, j);
           const uint32_t dl = meta & 0xFFFFu, de = ((meta >> 16) & 0xFFu) - ql;
-          const uint32_t c = (r >= r0 && r < r1) ? cnt[dl] : 0u;    // 0: outside the run or a removed doc
+          const uint32_t c = (r >= r0 && r < r1) ? cn[dl] : 0u;     // 0: outside the run or a removed doc
           dv[j] = doc_base + dl;
           some |= (c == 1u) ? (1u << j) : 0u;
           multi |= (c > 1u) ? (1u << j) : 0u;
-          if (c == 1u) cnt[dl] = 0u;                    // the doc's only row: clean for the next shard
+          if (c == 1u) cn[dl] = 0u;                     // the doc's only row: clean for the shard after next
           // zero_to_one.rs:44-126 for a doc with ONE event: max over the fields the term occurs in of
           // (s / tf) * tf / max(field_length, query_terms_len); table rows for tf = 0 hold +0.0
           double best = 0.0;
@@ -358,85 +394,105 @@ union_kernel(const __grid_constant__ UnionParams P) {
         if (capture) acc.template add4<true, true>(P.out, some, dv, sc, lane);
         else acc.template add4<false, true>(P.out, some, dv, sc, lane);
       }
-      __syncthreads();
-      PB_UPROF(2);
+    };
 
-      // ---- pass C: ZeroToOne::finalize (zero_to_one.rs:84-126) for the docs with several events: 32 listed docs
-      //      at a time per warp, one lane per doc.
-      {
-        const uint32_t nm = n_multi[par];
-        for (uint32_t base = warp * 32; base < nm; base += NW * 32) {
-          const bool valid = base + lane < nm;
-          const uint32_t d = valid ? mlist[base + lane] : 0u;
-          double result = 0.0;
-          if (valid) {
-            cnt[d] = 0u;                                                     // clean for the next shard
+    // ---- pass C: ZeroToOne::finalize (zero_to_one.rs:84-126) for the docs with several events: 32 listed docs
+    //      at a time per warp, one lane per doc.
+    auto pass_merge = [&](uint32_t sh, uint32_t buf) {
+      uint32_t* cn = cnt + buf * W;
+      const uint16_t* ml = mlist + buf * W;
+      const uint32_t doc_base = sh << P.uv.wbits;
+      const uint32_t nm = n_multi[buf];
+      // the warps take batches from the top so that the count pass of the next shard (taken from warp 0 up) meets them
+      for (uint32_t base = (NW - 1 - warp) * 32; base < nm; base += NW * 32) {
+        const bool valid = base + lane < nm;
+        const uint32_t d = valid ? ml[base + lane] : 0u;
+        double result = 0.0;
+        if (valid) {
+          cn[d] = 0u;                                                      // clean for the shard after next
 #pragma unroll
-            for (int f = 0; f < F; ++f) {
-              const uint4 k = top[f * W + d];
-              if ((k.x & k.y & k.z & k.w) == U_SENT) continue;
-              top[f * W + d] = SENT4;
-              uint4 k2 = SENT4;
-              if (GEN) { k2 = sec[f * W + d]; sec[f * W + d] = SENT4; }
-              const double2 my = mrc[max((uint32_t)flv[f * W + d], qtl)];   // zero_to_one.rs:119
-              uint32_t pm = (k.x != U_SENT ? 1u : 0u) | (k.y != U_SENT ? 2u : 0u) | (k.z != U_SENT ? 4u : 0u) | (k.w != U_SENT ? 8u : 0u);
-              bool pool = false;
-              if (GEN && (pm & (pm - 1u))) {
-                // a pool can only refuse an entry when two query terms hold the SAME expanded term
-                uint32_t tm[U_MAX_ACT];
+          for (int f = 0; f < F; ++f) {
+            const uint4 k = top[f * W + d];
+            if ((k.x & k.y & k.z & k.w) == U_SENT) continue;
+            top[f * W + d] = SENT4;
+            uint4 k2 = SENT4;
+            if (GEN) { k2 = sec[f * W + d]; sec[f * W + d] = SENT4; }
+            const double2 my = mrc[max((uint32_t)flv[f * W + d], qtl)];     // zero_to_one.rs:119
+            uint32_t pm = (k.x != U_SENT ? 1u : 0u) | (k.y != U_SENT ? 2u : 0u) | (k.z != U_SENT ? 4u : 0u) | (k.w != U_SENT ? 8u : 0u);
+            bool pool = false;
+            if (GEN && (pm & (pm - 1u))) {
+              // a pool can only refuse an entry when two query terms hold the SAME expanded term
+              uint32_t tm[U_MAX_ACT];
 #pragma unroll
-                for (int a = 0; a < U_MAX_ACT; ++a) tm[a] = uq.lo[a] + ((u4get(k, a) >> 6) & 0xFFFFFu);
+              for (int a = 0; a < U_MAX_ACT; ++a) tm[a] = uq.lo[a] + ((u4get(k, a) >> 6) & 0xFFFFFu);
 #pragma unroll
-                for (int a = 0; a < U_MAX_ACT; ++a)
+              for (int a = 0; a < U_MAX_ACT; ++a)
 #pragma unroll
-                  for (int c = a + 1; c < U_MAX_ACT; ++c)
-                    pool |= ((pm >> a) & (pm >> c) & 1u) && tm[a] == tm[c];
-              }
-              double accx = 0.0;
-              if (GEN && pool) {
-                accx = u_finalize_slow(vt, stab, uq, k, k2, my.x, my.y);
-              } else if (__popc(pm) <= 2) {
-                // <= 2 entries, no pool interaction: every query term accepts its best entry; a + b is commutative
-                // and 0.0 + x == x, so no ordering is needed
-                while (pm) {
-                  const int a = __ffs(pm) - 1;
-                  pm &= pm - 1u;
-                  accx = __dadd_rn(accx, u_div_m(u_entry_num(vt, uq, a, u4get(k, a)), my.x, my.y));
-                }
-              } else {
-                // 3 or 4 entries: (x + y) + z — added in the order of the reference's stable sort by score descending;
-                // absent terms sort last and add an exact +0.0
-                double s4[U_MAX_ACT], en[U_MAX_ACT];
-#pragma unroll
-                for (int a = 0; a < U_MAX_ACT; ++a) {
-                  const uint32_t key = u4get(k, a);
-                  s4[a] = -1.0; en[a] = 0.0;
-                  if (key != U_SENT) {
-                    const uint32_t e = key >> 26, ql = uq.qlen[a];
-                    s4[a] = (e - ql) < (uint32_t)U_DE ? stab[a * U_DE + (e - ql)] : z2o_term_score(e, ql);
-                    en[a] = u_div_m(u_entry_num(vt, uq, a, key), my.x, my.y);
-                  }
-                }
-                int rk[U_MAX_ACT];
-#pragma unroll
-                for (int a = 0; a < U_MAX_ACT; ++a) {
-                  rk[a] = 0;
-#pragma unroll
-                  for (int c = 0; c < U_MAX_ACT; ++c)
-                    if (c != a) rk[a] += (s4[c] > s4[a] || (s4[c] == s4[a] && c < a)) ? 1 : 0;
-                }
-#pragma unroll
-                for (int r = 0; r < U_MAX_ACT; ++r)
-                  accx = __dadd_rn(accx, rk[0] == r ? en[0] : rk[1] == r ? en[1] : rk[2] == r ? en[2] : en[3]);
-              }
-              result = fmax(accx, result);                                  // zero_to_one.rs:122
+                for (int c = a + 1; c < U_MAX_ACT; ++c)
+                  pool |= ((pm >> a) & (pm >> c) & 1u) && tm[a] == tm[c];
             }
+            double accx = 0.0;
+            if (GEN && pool) {
+              accx = u_finalize_slow(vt, stab, uq, k, k2, my.x, my.y);
+            } else if (__popc(pm) <= 2) {
+              // <= 2 entries, no pool interaction: every query term accepts its best entry; a + b is commutative
+              // and 0.0 + x == x, so no ordering is needed
+              while (pm) {
+                const int a = __ffs(pm) - 1;
+                pm &= pm - 1u;
+                accx = __dadd_rn(accx, u_div_m(u_entry_num(vt, uq, a, u4get(k, a)), my.x, my.y));
+              }
+            } else {
+              // 3 or 4 entries: (x + y) + z — added in the order of the reference's stable sort by score descending;
+              // absent terms sort last and add an exact +0.0
+              double s4[U_MAX_ACT], en[U_MAX_ACT];
+#pragma unroll
+              for (int a = 0; a < U_MAX_ACT; ++a) {
+                const uint32_t key = u4get(k, a);
+                s4[a] = -1.0; en[a] = 0.0;
+                if (key != U_SENT) {
+                  const uint32_t e = key >> 26, ql = uq.qlen[a];
+                  s4[a] = (e - ql) < (uint32_t)U_DE ? stab[a * U_DE + (e - ql)] : z2o_term_score(e, ql);
+                  en[a] = u_div_m(u_entry_num(vt, uq, a, key), my.x, my.y);
+                }
+              }
+              int rk[U_MAX_ACT];
+#pragma unroll
+              for (int a = 0; a < U_MAX_ACT; ++a) {
+                rk[a] = 0;
+#pragma unroll
+                for (int c = 0; c < U_MAX_ACT; ++c)
+                  if (c != a) rk[a] += (s4[c] > s4[a] || (s4[c] == s4[a] && c < a)) ? 1 : 0;
+              }
+#pragma unroll
+              for (int r = 0; r < U_MAX_ACT; ++r)
+                accx = __dadd_rn(accx, rk[0] == r ? en[0] : rk[1] == r ? en[1] : rk[2] == r ? en[2] : en[3]);
+            }
+            result = fmax(accx, result);                                    // zero_to_one.rs:122
           }
-          acc.add(P.out, valid, doc_base + d, result, lane);
         }
+        acc.add(P.out, valid, doc_base + d, result, lane);
       }
-      __syncthreads();
-      PB_UPROF(5);
+    };
+
+    {
+      Geo G, Gn;
+      uint32_t buf = 0;
+      uint32_t cur = next_shard(s0, G);
+      if (cur < s1) { pass_count(cur, G, buf); __syncthreads(); }
+      PB_UPROF(1);
+      while (cur < s1) {
+        if (tid == 0) n_multi[buf ^ 1u] = 0u;              // last read two barriers ago (merge of the previous shard)
+        pass_score(cur, G, buf);
+        __syncthreads();
+        PB_UPROF(2);
+        const uint32_t nxt = next_shard(cur + 1, Gn);
+        pass_merge(cur, buf);
+        if (nxt < s1) pass_count(nxt, Gn, buf ^ 1u);
+        __syncthreads();
+        PB_UPROF(5);
+        cur = nxt; G = Gn; buf ^= 1u;
+      }
     }
 
     // ---- item end: one partial result (count, digests, top-k) per item --------------------------------
