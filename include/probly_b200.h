@@ -128,7 +128,7 @@ typedef struct pb_index_image {
   const uint32_t* term_node;       /* [n_terms] */
   const uint32_t* post_blocks;     /* [n_rows_padded / 128][1 + 2F][128] tile-blocked columns */
   const uint64_t* doc_key;         /* [n_docs] ordinal -> caller's key */
-  const uint32_t* removed_bitmap;  /* [(n_docs + 31) / 32] bit set = not live */
+  const uint32_t* removed_bitmap;  /* [(n_docs + 31) / 32 + 1] words (one spare zero word), bit set = not live */
   uint64_t n_removed;
   uint64_t n_live_docs;
   double field_avg[PB_MAX_FIELDS];
@@ -137,8 +137,10 @@ int pb_builder_flatten(pb_builder* b, pb_index_image* out);
 
 /* On-disk / wire format of an image (the reference has no serialisation at all: no serde, the index
  * lives only in RAM — SURVEY §5, §8f-2).  One file = header + section table + 64-byte aligned
- * sections + FNV-1a checksum (layout: csrc/image_io.cpp).  pb_image_load validates magic, section
- * sizes against the header scalars and the checksum; the returned handle owns the buffer the
+ * sections + FNV-1a checksum over the header scalars and every section (layout: csrc/image_io.cpp).
+ * pb_image_load validates magic, scalar ranges, section sizes against the scalars, the checksum and the
+ * structure (monotone offsets, children / terms / doc ordinals in range, every (tf, field length) within
+ * max_tf / max_fl — the same pass pb_index_create runs on any image); the returned handle owns the buffer the
  * image's pointers point into, so a serving process needs no pb_builder:
  *   pb_image_load(path, &f); pb_index_create(pb_image_file_image(f), dev, &ix); pb_image_file_free(f); */
 typedef struct pb_image_file pb_image_file;

@@ -16,6 +16,9 @@ const char* get_error();
 
 bool utf8_valid(const uint8_t* p, size_t n);
 
+// structural validation of a flattened image (image_io.cpp): PB_OK or PB_ERR_INVALID + message
+int validate_image(const pb_index_image* im);
+
 }  // namespace pb
 
 // Nothing may throw across the C ABI (include/probly_b200.h "Errors").

@@ -1130,6 +1130,9 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
   }
   if (device < 0 || device >= ndev) { pb::set_error("pb_index_create: device %d out of range (0..%d)", device, ndev - 1); return PB_ERR_INVALID; }
   PB_TRY({
+    // the kernels index with the image's offsets / ordinals unchecked and the u16 posting codes are sized from
+    // max_tf / max_fl: refuse an inconsistent image here (PB_TRUST_IMAGE=1 skips the O(rows) pass)
+    if (!(std::getenv("PB_TRUST_IMAGE") && !std::strcmp(std::getenv("PB_TRUST_IMAGE"), "1"))) RC(pb::validate_image(im));
     CU(cudaSetDevice(device));
     pb_index* ix = new pb_index();
     std::unique_ptr<pb_index> guard(ix);

@@ -73,3 +73,78 @@ def test_corrupt_and_foreign_files_are_rejected(tmp_path):
     open(bad, "wb").write(hdr)
     assert load(bad) == capi.PB_ERR_INVALID
     assert load(str(tmp_path / "missing.pbimg")) == capi.PB_ERR_INVALID
+
+
+def test_header_scalars_are_covered_by_the_checksum(tmp_path):
+    """max_tf / max_fl / field_avg / n_live_docs size the device's u16 posting codes and the BM25 table: a flipped
+    bit there must not load (round-1 advisory: only the section payloads were summed)."""
+    ix = _index()
+    p = str(tmp_path / "ix.pbimg")
+    ix.save_image(p)
+    raw = bytearray(open(p, "rb").read())
+    L = capi.lib()
+    # scalar block starts at byte 16: u32 version, u32 num_fields, 6 x u64, u32 max_term_bytes, u32 pad, max_tf[4] ...
+    off_max_tf = 16 + 8 + 6 * 8 + 8
+    for off in (off_max_tf, off_max_tf + 16, off_max_tf + 32 + 8, off_max_tf + 32 + 16):      # max_tf[0], max_fl[0], n_live_docs, field_avg[0]
+        bad = bytearray(raw)
+        bad[off] ^= 0x01
+        q = str(tmp_path / "bad.pbimg")
+        open(q, "wb").write(bad)
+        h = C.c_void_p()
+        assert L.pb_image_load(os.fsencode(q), C.byref(h)) == capi.PB_ERR_INVALID, off
+
+
+def test_structurally_broken_images_are_refused():
+    """The kernels index with the image's offsets and ordinals unchecked: validate_image (run by pb_image_load and
+    by pb_index_create on any image) refuses out-of-range values instead of letting the device read out of bounds."""
+    L = capi.lib()
+    ix = _index()
+    im = ix.flatten()
+    p = "/tmp/pb_valid_probe.pbimg"
+
+    def save_rc(image):
+        return L.pb_image_save(C.byref(image), os.fsencode(p))
+
+    assert save_rc(im) == 0
+    h = C.c_void_p()
+    assert L.pb_image_load(os.fsencode(p), C.byref(h)) == 0
+    L.pb_image_file_free(h)
+
+    def broken(mutate):
+        """save a copy of the image with one array value changed, then try to load it"""
+        a = H.image_arrays(im)
+        keep = mutate(a)
+        try:
+            assert save_rc(im) == 0                  # saving does not validate the payload ...
+            hh = C.c_void_p()
+            rc = L.pb_image_load(os.fsencode(p), C.byref(hh))      # ... loading does
+            if rc == 0:
+                L.pb_image_file_free(hh)
+            return rc
+        finally:
+            keep()
+
+    def poke(arr, idx, val):
+        def m(a):
+            old = int(a[arr][idx])
+            a[arr][idx] = val
+            return lambda: a[arr].__setitem__(idx, old)
+        return m
+
+    def poke_block(word, val):                       # post_blocks is tile-blocked: word 0 = doc of row 0, word 128 = tf[0] of row 0
+        def m(a):
+            old = int(im.post_blocks[word])
+            im.post_blocks[word] = val
+            return lambda: im.post_blocks.__setitem__(word, old)
+        return m
+
+    nd, nn, nt = int(im.n_docs), int(im.n_nodes), int(im.n_terms)
+    assert broken(poke_block(0, nd + 5)) == capi.PB_ERR_INVALID and "doc ordinals" in capi.last_error()
+    assert broken(poke("edge_child", 0, nn)) == capi.PB_ERR_INVALID
+    assert broken(poke("term_row_begin", 1, 10**9)) == capi.PB_ERR_INVALID
+    assert broken(poke("node_term_hi", 0, nt + 1)) == capi.PB_ERR_INVALID
+    assert broken(poke_block(128, int(im.max_tf[0]) + 1)) == capi.PB_ERR_INVALID and "max_tf" in capi.last_error()
+    hh = C.c_void_p()
+    assert save_rc(im) == 0 and L.pb_image_load(os.fsencode(p), C.byref(hh)) == 0      # everything restored: loads again
+    L.pb_image_file_free(hh)
+    os.unlink(p)
