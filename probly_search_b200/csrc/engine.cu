@@ -312,6 +312,7 @@ struct pb_batch {
   DBuf<uint32_t> bitmap;
   size_t bitmap_zeroed = 0;
   DBuf<ull> rec_key, rec_val, rec_key2, rec_val2;
+  DBuf<uint8_t> rec_flags;
   // BM25 table
   DBuf<double> tab;
   uint32_t tab_tfcap[4] = {}, tab_flcap[4] = {}, tab_off[4] = {}, tab_total = 0;
@@ -649,6 +650,8 @@ int batch_compute(pb_batch* b) {
     up.min_rows = div ? ix->n_docs / div : 0;
   }
   up.uq = b->uq.p; up.q_isu = b->q_isu.p; up.q_isu2 = b->q_isu2.p;
+  up.max_term_bytes = ix->max_term_bytes;
+  for (uint32_t f = 0; f < ix->F; ++f) up.max_tf = std::max(up.max_tf, ix->max_tf[f]);
   up.allow_gen = union_smem_bytes((int)ix->F, ix->u_wbits, true) <= (226u << 10) ? 1u : 0u;
   if (union_smem_bytes((int)ix->F, ix->u_wbits, false) > (226u << 10)) up.enabled = 0;
   up.liverowcnt_prefix = ix->liverowcnt_prefix.p; up.dflive_prefix = ix->dflive_prefix.p;
@@ -951,7 +954,7 @@ int batch_compute(pb_batch* b) {
         if (h_over > legacy_cap) {
           legacy_cap = (uint64_t)h_over + h_over / 4 + 1024;
           CU(b->rec_key.ensure(legacy_cap)); CU(b->rec_val.ensure(legacy_cap));
-          CU(b->rec_key2.ensure(legacy_cap)); CU(b->rec_val2.ensure(legacy_cap));
+          CU(b->rec_key2.ensure(legacy_cap)); CU(b->rec_val2.ensure(legacy_cap)); CU(b->rec_flags.ensure(legacy_cap));
         }
         P.rec_key = b->rec_key.p; P.rec_val = b->rec_val.p; P.rec_cap = (uint32_t)legacy_cap;
         const int ef0 = b->rev_begin();
@@ -967,7 +970,7 @@ int batch_compute(pb_batch* b) {
           CU(cub::DeviceRadixSort::SortPairs(b->cub_temp.p, bytes, b->rec_key.p, b->rec_key2.p, b->rec_val.p, b->rec_val2.p,
                                              (int64_t)h_over, 0, end_bit, st));
           FoldParams FP;
-          FP.S = P; FP.key = b->rec_key2.p; FP.val = b->rec_val2.p; FP.n = h_over;
+          FP.S = P; FP.key = b->rec_key2.p; FP.val = b->rec_val2.p; FP.flags = b->rec_flags.p; FP.n = h_over;
           RC(launch_fold(b, FP));
           launches += 2 + (uint32_t)((end_bit + 7) / 8);
           S.legacy_records += h_over;
@@ -1023,7 +1026,6 @@ int batch_finish(pb_batch* b) {
   if (h_cnt[2] & 1u) { pb::set_error("internal: partial top-k list overflow"); return PB_ERR_INVALID; }
   if (h_cnt[2] & 2u) { pb::set_error("internal: side-path record buffer overflow"); return PB_ERR_INVALID; }
   if (h_cnt[2] & 8u) { pb::set_error("a query expands to more than 2^27 posting lists"); return PB_ERR_UNSUPPORTED; }
-  if (h_cnt[2] & 4u) { pb::set_error("a document received more than 64 (query term, expansion) events in one ZeroToOne query"); return PB_ERR_UNSUPPORTED; }
   S.rows_streamed = h_stats[ST_ROWS_STREAMED] + h_stats[ST_COUNT + ST_ROWS_STREAMED] + h_stats[2 * ST_COUNT + ST_ROWS_STREAMED];
   S.rows_scored = h_stats[ST_ROWS_SCORED] + h_stats[ST_COUNT + ST_ROWS_SCORED] + h_stats[2 * ST_COUNT + ST_ROWS_SCORED];
   S.pointer_visits = h_stats[ST_POINTER_VISITS] + h_stats[ST_COUNT + ST_POINTER_VISITS] + h_stats[2 * ST_COUNT + ST_POINTER_VISITS];

@@ -1076,6 +1076,7 @@ struct FoldParams {
   ScoreParams S;
   const unsigned long long* key;   // sorted
   const unsigned long long* val;
+  uint8_t* flags;                  // [n] scratch of the slow per-doc fold (docs with more than 32 events)
   uint32_t n;
 };
 
@@ -1137,18 +1138,19 @@ __device__ __noinline__ bool fold_group_slow(const FoldParams& FP, uint32_t i, u
     has = true;
     const uint32_t qtl = (uint32_t)(P.query_term_off[q + 1] - P.query_term_off[q]);
     const uint32_t ne = e - i;
+    uint8_t* fg = FP.flags + i;            // per event: bit 0 = looked at, bit 1 = accepted (this doc's slice of the scratch)
 #pragma unroll 1
     for (int x = 0; x < F; ++x) {
       double accx = 0.0;
-      unsigned long long done_lo = 0, acc_lo = 0;
+      for (uint32_t j = 0; j < ne; ++j) fg[j] = 0;
       for (uint32_t step = 0; step < ne; ++step) {
         int bj = -1; double bs = 0.0; unsigned long long bv = 0; uint32_t btf = 0, bfl = 0, bterm = 0, bqti = 0;
-        for (uint32_t j = 0; j < ne && j < 64; ++j) {
-          if ((done_lo >> j) & 1ull) continue;
+        for (uint32_t j = 0; j < ne; ++j) {
+          if (fg[j] & 1u) continue;
           unsigned long long v = FP.val[i + j];
           uint32_t row = (uint32_t)v;
           uint32_t tf = row_tf<F>(P.ix, row, x);
-          if (tf == 0) { done_lo |= 1ull << j; continue; }
+          if (tf == 0) { fg[j] |= 1u; continue; }
           const Seg sg = P.segs[(uint32_t)(v >> 32)];
           double sc = z2o_term_score(P.ix.term_byte_len[sg.term], sg.qlen);
           if (bj < 0 || sc > bs || (sc == bs && v < bv)) {
@@ -1156,21 +1158,20 @@ __device__ __noinline__ bool fold_group_slow(const FoldParams& FP, uint32_t i, u
           }
         }
         if (bj < 0) break;
-        done_lo |= 1ull << bj;
+        fg[bj] |= 1u;
         bool consumed = false; uint32_t used = 0;
-        for (uint32_t j = 0; j < ne && j < 64; ++j) {
-          if (!((acc_lo >> j) & 1ull)) continue;
+        for (uint32_t j = 0; j < ne; ++j) {
+          if (!(fg[j] & 2u)) continue;
           const Seg sg = P.segs[(uint32_t)(FP.val[i + j] >> 32)];
           consumed |= (sg.qti == bqti);
           used += (sg.term == bterm);
         }
         if (consumed || used >= btf) continue;
-        acc_lo |= 1ull << bj;
+        fg[bj] |= 2u;
         accx = __dadd_rn(accx, z2o_entry(P.ix, bs, btf, bfl, qtl));
       }
       result = fmax(accx, result);
     }
-    if (ne > 64) atomicOr(P.out.error_flag, 4u);   // > 64 events on one doc: outside the envelope
   }
   *out = result;
   return has;

@@ -105,6 +105,7 @@ __device__ __forceinline__ uint32_t first_live_term(const IndexView& ix, uint32_
 struct UPlan {
   uint32_t enabled;
   uint32_t allow_gen;                          // the two-candidate kernel fits shared memory at this field count
+  uint32_t max_term_bytes, max_tf;             // of the index: longest term, largest tf over all fields
   unsigned long long min_rows;                 // a class-U query streams at least this many rows
   UQuery* uq;                                  // [n_queries]
   unsigned long long* q_isu;                   // [n_queries + 1] class U without overlapping term ranges
@@ -171,6 +172,8 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
       const uint32_t lo = qt_lo[t], hi = qt_hi[t];
       if (ix.live_prefix[hi] == ix.live_prefix[lo]) continue;
       if (d.n_act == (uint32_t)U_MAX_ACT || hi - lo > (1u << 20) || qt_len[t] > 63u) { ok = false; break; }
+      // the kernel's (explen - qlen, tf) table must cover every row the query can meet
+      if (up.max_term_bytes - qt_len[t] >= (uint32_t)U_DE || up.max_tf >= (uint32_t)U_TF) { ok = false; break; }
       d.lo[d.n_act] = lo; d.hi[d.n_act] = hi; d.qti[d.n_act] = (uint8_t)(t - t0); d.qlen[d.n_act] = (uint8_t)qt_len[t];
       ++d.n_act;
     }

@@ -118,6 +118,13 @@ __device__ __forceinline__ void prefetch_group(const UnionView& uv, uint32_t grp
   else if (lane >= 8 && lane < 8 + 2 * F) prefetch_l1(uv.code[(lane - 8) >> 1] + base + ((lane - 8) & 1) * 64);
 }
 
+// max of two doubles that are >= +0.0 and finite: such doubles order like their bit patterns, so this is fmax without
+// the NaN / signed-zero handling an f64 max instruction sequence carries
+__device__ __forceinline__ double u_max_nonneg(double a, double b) {
+  const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+  return __longlong_as_double(ia > ib ? ia : ib);
+}
+
 __device__ __forceinline__ uint32_t u4get(const uint4& v, int a) { return a == 0 ? v.x : a == 1 ? v.y : a == 2 ? v.z : v.w; }
 
 // (s / tf) * tf for a candidate key of query term `a` (zero_to_one.rs:72, 117-118)
@@ -327,7 +334,6 @@ union_kernel(const __grid_constant__ UnionParams P) {
         const double* vta = vt + a * (U_DE * U_TF);
         uint32_t some = 0, multi = 0, dv[4];
         double sc[4];
-        bool oob = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t r = base + j;
@@ -345,29 +351,13 @@ union_kernel(const __grid_constant__ UnionParams P) {
           for (int f = 0; f < F; ++f) {
             const uint32_t code = __byte_perm(j < 2 ? c4[f].x : c4[f].y, 0u, (j & 1) ? 0x4432u : 0x4410u);
             const uint32_t tf = code >> P.ix.fl_bits[f], fl = code & ((1u << P.ix.fl_bits[f]) - 1u);
-            const bool in = de < (uint32_t)U_DE && tf < (uint32_t)U_TF;
-            oob |= !in && c == 1u;
-            const double v = vta[in ? de * U_TF + tf : 0u];
+            // class-U queries are only those whose (explen - qlen, tf) pairs all lie inside the table (plan_query_kernel);
+            // rows outside the run (c == 0) may index anywhere inside the table block: de is clamped
+            const double v = vta[min(de, (uint32_t)U_DE - 1u) * U_TF + tf];
             const double2 my = mrc[max(fl, qtl)];
-            best = fmax(u_div_m(v, my.x, my.y), best);
+            best = u_max_nonneg(u_div_m(v, my.x, my.y), best);
           }
           sc[j] = best;
-        }
-        if (__any_sync(0xffffffffu, oob)) {             // a (explen - qlen, tf) pair outside the table: real divisions
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (!((some >> j) & 1u)) continue;
-            const uint32_t e = (u4c(m4, j) >> 16) & 0xFFu;
-            const double s = z2o_term_score(e, ql);
-            double best = 0.0;
-#pragma unroll
-            for (int f = 0; f < F; ++f) {
-              const uint32_t code = __byte_perm(j < 2 ? c4[f].x : c4[f].y, 0u, (j & 1) ? 0x4432u : 0x4410u);
-              const uint32_t tf = code >> P.ix.fl_bits[f], fl = code & ((1u << P.ix.fl_bits[f]) - 1u);
-              if (tf > 0) best = fmax(z2o_entry(P.ix, s, tf, fl, qtl), best);
-            }
-            sc[j] = best;
-          }
         }
         if (multi) {
 #pragma unroll
