@@ -135,6 +135,18 @@ typedef struct pb_index_image {
 } pb_index_image;
 int pb_builder_flatten(pb_builder* b, pb_index_image* out);
 
+/* Incremental maintenance (the reference's add_document, src/index.rs:77-158, is cheap and
+ * this keeps it cheap): a DELTA segment is the image of the docs whose ordinal is >= from_doc_ordinal only —
+ * the CURRENT trie and term order (so expansion order is the global one, query.rs:109-147) with just those
+ * docs' posting rows.  A serving process keeps the big image resident, uploads the small delta image as a
+ * second pb_index, gives each of the two the other's per-term live counts (pb_index_set_df_extra: the
+ * reference has ONE posting list per term, so BM25's document frequency is the sum) and merges the
+ * per-query results, which are disjoint by document.  pb_builder_flatten_term_ids returns, for the image
+ * flattened last, the builder's stable term id of every term ordinal: the key that matches terms across
+ * segments.  The builder hands out ONE image at a time: a later flatten reuses its buffers. */
+int pb_builder_flatten_from(pb_builder* b, uint64_t from_doc_ordinal, pb_index_image* out);
+int pb_builder_flatten_term_ids(const pb_builder* b, uint32_t* out, uint64_t cap, uint64_t* n_terms);
+
 /* On-disk / wire format of an image (the reference has no serialisation at all: no serde, the index
  * lives only in RAM — SURVEY §5, §8f-2).  One file = header + section table + 64-byte aligned
  * sections + FNV-1a checksum over the header scalars and every section (layout: csrc/image_io.cpp).
@@ -160,6 +172,9 @@ int pb_index_create(const pb_index_image* image, int device, pb_index** out);
  * idf table (bm25.rs:41-56) on the host with libm log. */
 int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t n_removed,
                             uint64_t n_live_docs, const double* field_avg);
+/* Segmented index: live occurrence counts of every term of THIS image in the other segments ([n_terms], by term
+ * ordinal; n = 0 clears).  BM25's idf (bm25.rs:41-56) is recomputed from local + extra counts. */
+int pb_index_set_df_extra(pb_index* ix, const uint64_t* df_extra, uint64_t n);
 void pb_index_destroy(pb_index* ix);
 /* expand_term (query.rs:109-126) through the device descent kernel: the expansions of `term`
  * joined by '\n' into out (cap bytes).  *n_expansions / *needed are always set. */

@@ -200,6 +200,8 @@ struct Builder {
 
   // flatten outputs (owned here, handed out as raw pointers)
   bool flat_valid = false;
+  uint64_t flat_from = 0;                // first doc ordinal whose rows the flattened image holds (0 = all: the full image)
+  std::vector<uint32_t> f_term_id;       // DFS term ordinal of the last flatten -> builder term id (stable across flattens)
   std::vector<uint32_t> f_node_edge_begin, f_node_term_lo, f_node_term_hi, f_node_parent, f_node_char;
   std::vector<uint32_t> f_edge_char, f_edge_child;
   std::vector<uint64_t> f_term_row_begin;
@@ -303,7 +305,6 @@ struct Builder {
   int remove_document(uint64_t key) {
     uint32_t ord = key2ord.get(key);
     if (ord == U64Map::npos) return PB_OK;            // unknown key: the reference does nothing either
-    flat_valid = false;
     removed_keys.put(key, ord);
     double new_len = (double)(n_live - 1);
     for (uint32_t f = 0; f < F; ++f) {
@@ -317,6 +318,14 @@ struct Builder {
     key2ord.erase(key);
     --n_live;
     ++n_removed_pending;
+    // Removal is lazy in the reference too (the postings stay until vacuum): the flattened structure is
+    // untouched, only the image's live state follows — O(1), no re-flatten of the posting columns.
+    if (flat_valid) {
+      f_removed[ord >> 5] |= 1u << (ord & 31);
+      image.n_removed = n_removed_pending;
+      image.n_live_docs = n_live;
+      for (uint32_t f = 0; f < F; ++f) image.field_avg[f] = field_avg[f];
+    }
     return PB_OK;
   }
 
@@ -380,18 +389,31 @@ struct Builder {
     for (uint32_t f = 0; f < F; ++f) { o->field_sum[f] = field_sum[f]; o->field_avg[f] = field_avg[f]; }
   }
 
-  int flatten(pb_index_image* out) {
-    if (!flat_valid) {
-      int rc = do_flatten();
+  // from_doc = 0: the whole index.  from_doc > 0: a DELTA segment — the current trie (so that its expansion order is
+  // the global one) with the posting rows of the docs whose ordinal is >= from_doc only.
+  int flatten(pb_index_image* out, uint64_t from_doc = 0) {
+    if (from_doc > doc_key.size()) { set_error("flatten: first doc ordinal %llu beyond the index", (unsigned long long)from_doc); return PB_ERR_INVALID; }
+    if (!flat_valid || flat_from != from_doc) {
+      flat_valid = false;
+      int rc = do_flatten(from_doc);
       if (rc != PB_OK) return rc;
       flat_valid = true;
+      flat_from = from_doc;
     }
     *out = image;
     return PB_OK;
   }
 
-  int do_flatten() {
+  int do_flatten(uint64_t from_doc) {
     const size_t NN = nodes.size();
+    // rows per term inside the flattened doc range
+    const uint64_t log_from = doc_log_begin[from_doc];
+    std::vector<uint64_t> rows_local;
+    if (from_doc) {
+      rows_local.assign(dict.size(), 0);
+      for (uint64_t i = log_from; i < log.size(); ++i) ++rows_local[log[i].term];
+    }
+    const std::vector<uint64_t>& rows_of = from_doc ? rows_local : term_rows;
     // children per parent, most recently created first (ids descend)
     std::vector<uint32_t> cnt(NN + 1, 0);
     for (size_t i = 1; i < NN; ++i) if (nodes[i].alive) ++cnt[nodes[i].parent + 1];
@@ -419,7 +441,7 @@ struct Builder {
       const Node& nd = nodes[old];
       f_node_char[id] = nd.ch;
       f_node_parent[id] = nd.parent == NONE ? NONE : new_id[nd.parent];
-      if (nd.term != NONE && term_rows[nd.term] > 0) {       // first_doc.is_some() (query.rs:136)
+      if (nd.term != NONE && rows_of[nd.term] > 0) {         // first_doc.is_some() (query.rs:136)
         f_term_node.push_back(id);
         f_term_byte_len.push_back((uint32_t)dict.str(nd.term).size());
         term_old.push_back(nd.term);
@@ -461,16 +483,18 @@ struct Builder {
     std::vector<uint32_t> ord_of(dict.size(), NONE);
     for (size_t t = 0; t < NT; ++t) ord_of[term_old[t]] = (uint32_t)t;
     f_term_row_begin.assign(NT + 1, 0);
-    for (size_t t = 0; t < NT; ++t) f_term_row_begin[t + 1] = f_term_row_begin[t] + term_rows[term_old[t]];
+    for (size_t t = 0; t < NT; ++t) f_term_row_begin[t + 1] = f_term_row_begin[t] + rows_of[term_old[t]];
     const uint64_t NR = f_term_row_begin[NT];
-    if (NR != log.size()) { set_error("flatten: internal row count mismatch"); return PB_ERR_INVALID; }
+    if (NR != log.size() - log_from) { set_error("flatten: internal row count mismatch"); return PB_ERR_INVALID; }
+    f_term_id = term_old;
     const uint64_t NRP = ((NR + 127) / 128 + 1) * 128;     // pad: whole 128-row tiles + one spare tile
     const uint32_t NCOL = 1 + 2 * F;
     f_post_blocks.assign(NRP * NCOL, 0);
     uint32_t max_tf[PB_MAX_FIELDS] = {0, 0, 0, 0}, max_fl[PB_MAX_FIELDS] = {0, 0, 0, 0};
     {
       std::vector<uint64_t> fill(f_term_row_begin.begin(), f_term_row_begin.end() - 1);
-      for (const Tuple& tp : log) {
+      for (uint64_t li = log_from; li < log.size(); ++li) {
+        const Tuple& tp = log[li];
         uint64_t r = fill[ord_of[tp.term]]++;
         uint32_t* blk = f_post_blocks.data() + (r / 128) * (uint64_t)NCOL * 128 + (r % 128);
         blk[0] = tp.doc;
@@ -487,8 +511,8 @@ struct Builder {
     const size_t ND = doc_key.size();
     f_removed.assign((ND + 31) / 32 + 1, 0);
     uint64_t nrem = 0;
-    for (size_t d = 0; d < ND; ++d)
-      if (doc_state[d] != LIVE) { f_removed[d >> 5] |= 1u << (d & 31); ++nrem; }
+    for (size_t d = 0; d < ND; ++d)      // ordinals vacuum left behind (GONE) own no posting row: only pending removals need the mask
+      if (doc_state[d] == REMOVED_PENDING) { f_removed[d >> 5] |= 1u << (d & 31); ++nrem; }
 
     pb_index_image& im = image;
     std::memset(&im, 0, sizeof(im));
@@ -567,6 +591,20 @@ int pb_builder_vacuum(pb_builder* b) {
 int pb_builder_get_info(const pb_builder* b, pb_builder_info* out) {
   if (!b || !out) return PB_ERR_INVALID;
   PB_TRY({ b->impl.info(out); return PB_OK; });
+}
+
+int pb_builder_flatten_from(pb_builder* b, uint64_t from_doc_ordinal, pb_index_image* out) {
+  if (!b || !out) { pb::set_error("pb_builder_flatten_from: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({ return b->impl.flatten(out, from_doc_ordinal); });
+}
+
+int pb_builder_flatten_term_ids(const pb_builder* b, uint32_t* out, uint64_t cap, uint64_t* n_terms) {
+  if (!b || !n_terms) { pb::set_error("pb_builder_flatten_term_ids: null argument"); return PB_ERR_INVALID; }
+  if (!b->impl.flat_valid) { pb::set_error("pb_builder_flatten_term_ids: no flattened image (call pb_builder_flatten first)"); return PB_ERR_INVALID; }
+  *n_terms = b->impl.f_term_id.size();
+  if (cap < b->impl.f_term_id.size()) { pb::set_error("pb_builder_flatten_term_ids: need %llu entries", (unsigned long long)b->impl.f_term_id.size()); return PB_ERR_CAPACITY; }
+  if (out && !b->impl.f_term_id.empty()) std::memcpy(out, b->impl.f_term_id.data(), b->impl.f_term_id.size() * sizeof(uint32_t));
+  return PB_OK;
 }
 
 int pb_builder_flatten(pb_builder* b, pb_index_image* out) {

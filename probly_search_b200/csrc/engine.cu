@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -54,7 +55,7 @@ struct DBuf {
     p = nullptr; cap = 0;
     size_t c = n + n / 8 + 64;
     cudaError_t e = cudaMalloc((void**)&p, c * sizeof(T));
-    if (e == cudaSuccess) cap = c;
+    if (e == cudaSuccess) { cap = c; e = cudaMemset(p, 0, c * sizeof(T)); }     // defined contents: slack and unused slots are copied / scanned
     return e;
   }
   // grow, keeping the first `keep` elements (device-to-device copy on `st`)
@@ -64,6 +65,8 @@ struct DBuf {
     T* np_ = nullptr;
     cudaError_t e = cudaMalloc((void**)&np_, c * sizeof(T));
     if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(np_, 0, c * sizeof(T), st);
+    if (e != cudaSuccess) { cudaFree(np_); return e; }
     if (p && keep) e = cudaMemcpyAsync(np_, p, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (p) cudaFree(p);
@@ -127,10 +130,12 @@ struct pb_index {
   DBuf<ull> liverowcnt_prefix, dflive_prefix;   // per-term prefixes of term_live_rows / term_df_live (class-U row statistics)
   // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
   std::vector<uint32_t> h_node_parent, h_node_char, h_term_node;
-  std::vector<uint64_t> h_term_row_begin, h_df_live;
+  std::vector<uint64_t> h_term_row_begin, h_df_live, h_df_extra;
   uint64_t n_live = 0, n_removed = 0;
   double avg[4] = {0, 0, 0, 0};
   uint64_t live_epoch = 0;       // bumped by every pb_index_set_live_state: staged batches rebuild their BM25 table
+  std::mutex occ_mu;             // guards occ_cache
+  std::map<uint64_t, int> occ_cache;   // resident CTAs per SM of a scoring-kernel shape
   std::mutex mu;                 // guards `scratch`
   pb_batch* scratch = nullptr;   // reused by pb_query_batch / pb_query_full / expand_term
 
@@ -205,6 +210,25 @@ static int index_build_union(pb_index* ix) {
   return PB_OK;
 }
 
+// BM25::before_each, bm25.rs:41-56: idf from the LIVE doc count and the clamped live df.
+// libm `log` on the host = what Rust's f64::ln calls, so the table is bit-identical.
+// h_df_extra (pb_index_set_df_extra): live occurrences of the same term in the OTHER segments of a segmented index —
+// the reference counts one posting list per term, so the document frequency is the sum over the segments.
+static int index_upload_idf(pb_index* ix) {
+  const size_t NT = ix->n_terms;
+  const bool extra = ix->h_df_extra.size() == NT;
+  std::vector<double> idf(NT + 1, 0.0);
+  for (size_t t = 0; t < NT; ++t) {
+    const uint64_t df = ix->h_df_live[t] + (extra ? ix->h_df_extra[t] : 0);
+    const uint64_t frequency = std::min<uint64_t>(ix->n_live, df);
+    const uint64_t diff = ix->n_live - frequency;
+    idf[t] = std::log(1.0 + ((double)diff + 0.5) / ((double)frequency + 0.5));
+  }
+  CU(ix->term_idf.ensure(NT + 1));
+  CU(cudaMemcpy(ix->term_idf.p, idf.data(), (NT + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  return PB_OK;
+}
+
 static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, uint64_t n_removed,
                                   uint64_t n_live, const double* avg) {
   CU(cudaSetDevice(ix->device));
@@ -230,16 +254,10 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
   }
   ix->h_df_live.assign(NT + 1, 0);
   CU(cudaMemcpy(ix->h_df_live.data(), ix->term_df_live.p, NT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  // BM25::before_each, bm25.rs:41-56: idf from the LIVE doc count and the clamped live df.
-  // libm `log` on the host = what Rust's f64::ln calls, so the table is bit-identical.
-  std::vector<double> idf(NT + 1, 0.0);
   std::vector<uint32_t> lp(NT + 2, 0);
   std::vector<uint64_t> lrp(NT + 2, 0);
   for (size_t t = 0; t < NT; ++t) {
     uint64_t df = ix->h_df_live[t];
-    uint64_t frequency = std::min<uint64_t>(n_live, df);
-    uint64_t diff = n_live - frequency;
-    idf[t] = std::log(1.0 + ((double)diff + 0.5) / ((double)frequency + 0.5));
     lp[t + 1] = lp[t] + (df > 0 ? 1u : 0u);
     lrp[t + 1] = lrp[t] + (df > 0 ? (ix->h_term_row_begin[t + 1] - ix->h_term_row_begin[t]) : 0);
   }
@@ -252,7 +270,7 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
     CU(cudaMemcpy(ix->liverowcnt_prefix.p, lrc.data(), (NT + 1) * sizeof(ull), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ix->dflive_prefix.p, dfp.data(), (NT + 1) * sizeof(ull), cudaMemcpyHostToDevice));
   }
-  CU(cudaMemcpy(ix->term_idf.p, idf.data(), (NT + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  RC(index_upload_idf(ix));
   CU(cudaMemcpy(ix->live_prefix.p, lp.data(), (NT + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ix->liverows_prefix.p, lrp.data(), (NT + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
   return PB_OK;
@@ -273,7 +291,6 @@ struct pb_batch {
   uint64_t full_cap = 0;
   DBuf<uint32_t> full_q, full_doc;
   DBuf<double> full_score;
-  DBuf<ull> full_count;
   // inputs
   DBuf<uint8_t> term_bytes;
   DBuf<uint64_t> term_byte_off, query_term_off;
@@ -281,7 +298,6 @@ struct pb_batch {
   DBuf<uint32_t> qt_lo, qt_hi, qt_len, qt_q;
   DBuf<ull> qt_gcount, qt_goff, q_isg, q_gidx, q_grows, q_prim, q_recbound, q_recoff, q_nbins, q_binoff, q_gsegoff, q_gtileoff, q_bmwords, q_bmoff;
   DBuf<uint8_t> q_scheme, q_shift;
-  DBuf<ull> xcount;
   DBuf<uint32_t> bin_count, bin_off, bin_cursor;
   DBuf<uint4> rec;
   DBuf<ull> s_tiles, s_tile_off, g_tiles, g_tile_off, g_mtiles, g_mtile_off;
@@ -302,11 +318,22 @@ struct pb_batch {
   bool gather_pending = false, gathered = false;
   uint64_t tab_epoch = 0;       // ix->live_epoch the BM25 table was built for
   // partial lists + counters
-  DBuf<uint32_t> part_head, part_next, part_n, part_doc, counters;   // counters: [0] part_count [1] rec_count [2] error
+  DBuf<uint32_t> part_head, part_next, part_n, part_doc;
   DBuf<double> part_score;
-  DBuf<ull> stats;            // [3][ST_COUNT]: S phase, G phase, U (union) phase
+  // every small counter of a run lives in ONE arena (one memset per run, one D2H for the stats):
+  //   counters [8 x u32]: [0] part_count [1] rec_count [2] error [3] overflow   stats [3][ST_COUNT]: S, G, U phase
+  //   u_counter [8]: union work-item counters + cycle profile   full_count [2]   xcount [4]
+  template <class T> struct View { T* p = nullptr; };
+  DBuf<ull> scal;
+  static constexpr size_t SCAL_WORDS = 4 + 3 * ST_COUNT + 8 + 2 + 4;
+  View<uint32_t> counters;
+  View<ull> stats, u_counter, full_count, xcount;
+  void* h_stage = nullptr;     // pinned staging for small result blocks (pb_query_batch: one D2H instead of six)
+  size_t h_stage_bytes = 0;
+  bool tab_valid = false;      // the BM25 table on the device matches (tab_k1, tab_b, tab_epoch)
+  double tab_k1 = 0, tab_b = 0;
   DBuf<UQuery> uq;
-  DBuf<ull> q_isu, q_uidx, q_isu2, q_uidx2, u_counter;
+  DBuf<ull> q_isu, q_uidx, q_isu2, q_uidx2;
   DBuf<uint32_t> u_list, u_list2;
   // side path
   DBuf<uint32_t> bitmap;
@@ -340,6 +367,7 @@ struct pb_batch {
     if (ix) cudaSetDevice(ix->device);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : rev) cudaEventDestroy(e);
+    if (h_stage) cudaFreeHost(h_stage);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -446,7 +474,7 @@ int batch_build_table(pb_batch* b) {
   return PB_OK;
 }
 
-int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
+int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap, bool sync_inputs = true) {
   pb_index* ix = b->ix;
   if (!d || (d->n_queries && (!d->query_term_off || !d->term_byte_off))) { pb::set_error("query batch: null argument"); return PB_ERR_INVALID; }
   if (d->scorer != PB_SCORER_BM25 && d->scorer != PB_SCORER_ZERO_TO_ONE) {
@@ -492,22 +520,27 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap) {
   CU(b->qt_gcount.ensure(NT + 2)); CU(b->qt_goff.ensure(NT + 2));
   CU(b->q_isg.ensure(Q + 2)); CU(b->q_gidx.ensure(Q + 2)); CU(b->q_grows.ensure(Q + 2)); CU(b->q_prim.ensure(Q + 2));
   CU(b->q_recbound.ensure(Q + 2)); CU(b->q_recoff.ensure(Q + 2)); CU(b->q_nbins.ensure(Q + 2)); CU(b->q_binoff.ensure(Q + 2));
-  CU(b->q_scheme.ensure(Q + 2)); CU(b->q_shift.ensure(Q + 2)); CU(b->xcount.ensure(4)); CU(b->q_bmwords.ensure(Q + 2)); CU(b->q_bmoff.ensure(Q + 2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
+  CU(b->q_scheme.ensure(Q + 2)); CU(b->q_shift.ensure(Q + 2)); CU(b->q_bmwords.ensure(Q + 2)); CU(b->q_bmoff.ensure(Q + 2)); CU(b->q_gsegoff.ensure(Q + 2)); CU(b->q_gtileoff.ensure(Q + 2));
   CU(b->s_tiles.ensure(Q + 2)); CU(b->s_tile_off.ensure(Q + 2));
   CU(b->seg_s.ensure(Q + 1));
   RC(batch_layout_results(b));
   CU(b->part_head.ensure(Q + 1));
-  CU(b->counters.ensure(8));
-  CU(b->stats.ensure(3 * ST_COUNT));
+  CU(b->scal.ensure(pb_batch::SCAL_WORDS));
+  b->counters.p = reinterpret_cast<uint32_t*>(b->scal.p);
+  b->stats.p = b->scal.p + 4; b->u_counter.p = b->stats.p + 3 * ST_COUNT; b->full_count.p = b->u_counter.p + 8;
+  b->xcount.p = b->full_count.p + 2;
   CU(b->uq.ensure(Q + 1)); CU(b->q_isu.ensure(Q + 2)); CU(b->q_uidx.ensure(Q + 2)); CU(b->u_list.ensure(Q + 1));
-  CU(b->q_isu2.ensure(Q + 2)); CU(b->q_uidx2.ensure(Q + 2)); CU(b->u_list2.ensure(Q + 1)); CU(b->u_counter.ensure(8));
+  CU(b->q_isu2.ensure(Q + 2)); CU(b->q_uidx2.ensure(Q + 2)); CU(b->u_list2.ensure(Q + 1));
   if (full_cap) {
     CU(b->full_q.ensure(full_cap)); CU(b->full_doc.ensure(full_cap)); CU(b->full_score.ensure(full_cap));
   }
-  CU(b->full_count.ensure(2));
-  if (b->scorer == PB_SCORER_BM25) RC(batch_build_table(b));
-  b->tab_epoch = ix->live_epoch;
-  CU(cudaStreamSynchronize(b->stream));   // caller buffers may be reused after return
+  if (b->scorer == PB_SCORER_BM25 &&
+      !(b->tab_valid && b->tab_k1 == b->k1 && b->tab_b == b->b && b->tab_epoch == ix->live_epoch)) {
+    RC(batch_build_table(b));             // (k1, b, avg) unchanged since the last batch staged here: the table stays
+    b->tab_valid = true; b->tab_k1 = b->k1; b->tab_b = b->b;
+    b->tab_epoch = ix->live_epoch;
+  }
+  if (sync_inputs) CU(cudaStreamSynchronize(b->stream));   // caller buffers may be reused after return
   b->loaded = true;
   b->ran = false;
   return PB_OK;
@@ -544,7 +577,18 @@ int launch_score(pb_batch* b, ScoreParams& P, bool gmode, uint64_t tiles) {
   P.tab_stride = 8u << sp.rep_shift;
   for (int x = 0; x < 4; ++x) P.tab_boff[x] = P.tab_off[x] * P.tab_stride;
   int per_sm = 1;
-  CU(ops->score_occupancy(sc, gmode, nw, &per_sm, sp.threads, sp.smem));
+  {
+    // cudaFuncSetAttribute + the occupancy query cost several microseconds per launch: remembered per shape
+    const uint64_t key = ((uint64_t)sp.smem << 16) | ((uint64_t)sp.threads << 4) | (sc ? 4u : 0u) | (gmode ? 2u : 0u) | (nw ? 1u : 0u);
+    std::lock_guard<std::mutex> lk(b->ix->occ_mu);
+    auto it = b->ix->occ_cache.find(key);
+    if (it == b->ix->occ_cache.end()) {
+      CU(ops->score_occupancy(sc, gmode, nw, &per_sm, sp.threads, sp.smem));
+      b->ix->occ_cache[key] = per_sm;
+    } else {
+      per_sm = it->second;
+    }
+  }
   if (per_sm < 1) { pb::set_error("scoring kernel does not fit an SM (%d threads, %zu B shared)", sp.threads, sp.smem); return PB_ERR_CUDA; }
   // one warp = one contiguous span of tiles; never more warps than there is work for
   const uint64_t warps_per_cta = (uint64_t)sp.threads / 32;
@@ -606,6 +650,7 @@ int batch_compute(pb_batch* b) {
   if (b->scorer == PB_SCORER_BM25 && b->tab_epoch != ix->live_epoch) {     // pb_index_set_live_state since staging: new avg
     RC(batch_build_table(b));
     b->tab_epoch = ix->live_epoch;
+    b->tab_valid = true; b->tab_k1 = b->k1; b->tab_b = b->b;
   }
   CU(cudaSetDevice(ix->device));
   cudaStream_t st = b->stream;
@@ -620,11 +665,7 @@ int batch_compute(pb_batch* b) {
   CU(cudaEventRecord(b->ev[0], st));
   CU(cudaMemsetAsync(b->res.p, 0, b->block_bytes, st));      // counts, digests, top-k: one packed block
   CU(cudaMemsetAsync(b->part_head.p, 0xFF, (Q + 1) * sizeof(uint32_t), st));
-  CU(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(uint32_t), st));
-  CU(cudaMemsetAsync(b->stats.p, 0, 3 * ST_COUNT * sizeof(ull), st));
-  CU(cudaMemsetAsync(b->u_counter.p, 0, 8 * sizeof(ull), st));
-  CU(cudaMemsetAsync(b->q_prim.p, 0, (Q + 2) * sizeof(ull), st));
-  CU(cudaMemsetAsync(b->full_count.p, 0, 2 * sizeof(ull), st));
+  CU(cudaMemsetAsync(b->scal.p, 0, pb_batch::SCAL_WORDS * sizeof(ull), st));   // counters, stats, work-item counters
   if (Q == 0) {
     for (int i = 1; i <= 5; ++i) CU(cudaEventRecord(b->ev[i], st));
     b->launches = 0;
@@ -658,19 +699,15 @@ int batch_compute(pb_batch* b) {
   up.stats = b->stats.p + 2 * ST_COUNT;
   plan_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(view, Q, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p,
                                                                  b->qt_len.p, b->seg_s.p, b->s_tiles.p, b->qt_gcount.p,
-                                                                 b->qt_q.p, b->q_isg.p, b->q_grows.p, b->stats.p, up);
+                                                                 b->qt_q.p, b->q_isg.p, b->q_grows.p, b->stats.p, up, NT);
   CU(cudaGetLastError());
   ++launches;
   // the exclusive scans below run over n + 1 entries: give the extra input entry a defined value
-  CU(cudaMemsetAsync(b->s_tiles.p + Q, 0, sizeof(ull), st));
-  CU(cudaMemsetAsync(b->qt_gcount.p + NT, 0, sizeof(ull), st));
   RC(scan_ull(b, b->s_tiles.p, b->s_tile_off.p, Q + 1));
   RC(scan_ull(b, b->qt_gcount.p, b->qt_goff.p, NT + 1));
   launches += 2;
   ull h_nu = 0, h_nu2 = 0;            // class-U queries: without / with overlapping term ranges
   if (up.enabled) {
-    CU(cudaMemsetAsync(b->q_isu.p + Q, 0, sizeof(ull), st));
-    CU(cudaMemsetAsync(b->q_isu2.p + Q, 0, sizeof(ull), st));
     RC(scan_ull(b, b->q_isu.p, b->q_uidx.p, Q + 1));
     RC(scan_ull(b, b->q_isu2.p, b->q_uidx2.p, Q + 1));
     launches += 2;
@@ -697,6 +734,7 @@ int batch_compute(pb_batch* b) {
     CU(b->g_tiles.ensure(n_gsegs + 2));
     CU(b->g_tile_off.ensure(n_gsegs + 2));
     CU(b->g_mtiles.ensure(n_gsegs + 2)); CU(b->g_mtile_off.ensure(n_gsegs + 2));
+    CU(cudaMemsetAsync(b->q_prim.p, 0, (Q + 2) * sizeof(ull), st));      // gfill elects the primary list with atomicMax
     gfill_kernel<<<ix->sm_count * 8, 256, 0, st>>>(view, NT, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p, b->qt_len.p,
                                                    b->qt_q.p, b->qt_gcount.p, b->qt_goff.p, b->seg_g.p, b->g_tiles.p,
                                                    b->q_prim.p, b->stats.p + ST_COUNT);
@@ -1015,14 +1053,14 @@ int batch_finish(pb_batch* b) {
   cudaStream_t st = b->stream;
   pb_batch_stats& S = b->st;
   CU(cudaSetDevice(ix->device));
-  ull h_stats[3 * ST_COUNT];
-  uint32_t h_cnt[4] = {0, 0, 0, 0};
-  ull h_full[2] = {0, 0};
-  CU(cudaMemcpyAsync(h_full, b->full_count.p, sizeof(h_full), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_stats, b->stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_cnt, b->counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  ull h_scal[pb_batch::SCAL_WORDS];
+  CU(cudaMemcpyAsync(h_scal, b->scal.p, sizeof(h_scal), cudaMemcpyDeviceToHost, st));      // counters + stats in one copy
   CU(cudaEventRecord(b->ev[8], st));
   CU(cudaStreamSynchronize(st));
+  uint32_t h_cnt[4];
+  std::memcpy(h_cnt, h_scal, sizeof(h_cnt));
+  const ull* h_stats = h_scal + 4;
+  const ull* h_full = h_scal + 4 + 3 * ST_COUNT + 8;
   if (h_cnt[2] & 1u) { pb::set_error("internal: partial top-k list overflow"); return PB_ERR_INVALID; }
   if (h_cnt[2] & 2u) { pb::set_error("internal: side-path record buffer overflow"); return PB_ERR_INVALID; }
   if (h_cnt[2] & 8u) { pb::set_error("a query expands to more than 2^27 posting lists"); return PB_ERR_UNSUPPORTED; }
@@ -1051,8 +1089,7 @@ int batch_finish(pb_batch* b) {
   }
   S.rows_streamed_side = h_stats[ST_COUNT + ST_ROWS_STREAMED];
   if (std::getenv("PB_UNION_PROF") && S.union_queries) {
-    ull h_prof[6] = {0, 0, 0, 0, 0, 0};
-    CU(cudaMemcpy(h_prof, b->u_counter.p + 2, sizeof(h_prof), cudaMemcpyDeviceToHost));
+    const ull* h_prof = h_scal + 4 + 3 * ST_COUNT + 2;
     fprintf(stderr, "[pb] union kernel cycles (thread 0 of every CTA): setup %llu count %llu score %llu merge-docs %llu item-end %llu, items %llu\n",
             h_prof[0], h_prof[1], h_prof[2], h_prof[5], h_prof[3], h_prof[4]);
   }
@@ -1083,9 +1120,18 @@ int batch_new(pb_index* ix, pb_batch** out) {
   return PB_OK;
 }
 
+int batch_fetch_enqueue(pb_batch* b, pb_query_results* o);
+
 int batch_fetch(pb_batch* b, pb_query_results* o) {
   if (!b->ran) { pb::set_error("pb_batch_fetch: batch has not been run"); return PB_ERR_INVALID; }
   CU(cudaSetDevice(b->ix->device));
+  RC(batch_fetch_enqueue(b, o));
+  CU(cudaStreamSynchronize(b->stream));
+  return PB_OK;
+}
+
+// the device-to-host copies of the per-query results, enqueued on the batch's stream (no wait)
+int batch_fetch_enqueue(pb_batch* b, pb_query_results* o) {
   const uint64_t Q = b->Q;
   cudaStream_t st = b->stream;
   if (Q) {
@@ -1096,7 +1142,6 @@ int batch_fetch(pb_batch* b, pb_query_results* o) {
     if (b->k && o->topk_doc) CU(cudaMemcpyAsync(o->topk_doc, b->topk_doc, Q * b->k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (b->k && o->topk_score) CU(cudaMemcpyAsync(o->topk_score, b->topk_score, Q * b->k * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
-  CU(cudaStreamSynchronize(st));
   return PB_OK;
 }
 
@@ -1244,6 +1289,18 @@ int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t
       bm[d >> 5] |= 1u << (d & 31);
     }
     return index_apply_live_state(ix, bm.data(), distinct, n_live_docs, field_avg);
+  });
+}
+
+int pb_index_set_df_extra(pb_index* ix, const uint64_t* df_extra, uint64_t n) {
+  if (!ix || (n && !df_extra)) { pb::set_error("pb_index_set_df_extra: null argument"); return PB_ERR_INVALID; }
+  if (n != 0 && n != ix->n_terms) { pb::set_error("pb_index_set_df_extra: %llu entries, the image has %llu terms", (ull)n, (ull)ix->n_terms); return PB_ERR_INVALID; }
+  PB_TRY({
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    ix->h_df_extra.assign(df_extra, df_extra + n);
+    ++ix->live_epoch;
+    return index_upload_idf(ix);
   });
 }
 
@@ -1493,9 +1550,37 @@ int pb_query_batch(pb_index* ix, const pb_query_batch_desc* q, pb_query_results*
     std::lock_guard<std::mutex> lk(ix->mu);
     pb_batch* b = nullptr;
     RC(index_scratch(ix, &b));
-    RC(batch_load(b, q, 0));
-    RC(batch_run(b));
-    return batch_fetch(b, out);
+    // one call = upload + kernels + download with as few host round trips as the planning allows: the caller's
+    // buffers stay valid for the whole call, so nothing waits for the uploads, and the result copies are
+    // enqueued BEFORE the run's final synchronisation (small batches: one copy of the packed block into a pinned
+    // staging buffer instead of six)
+    RC(batch_load(b, q, 0, false));
+    RC(batch_compute(b));
+    const bool staged = b->Q && b->block_bytes <= (1u << 20);
+    if (staged) {
+      if (b->h_stage_bytes < b->block_bytes) {
+        if (b->h_stage) cudaFreeHost(b->h_stage);
+        b->h_stage = nullptr; b->h_stage_bytes = 0;
+        CU(cudaMallocHost(&b->h_stage, b->block_bytes));
+        b->h_stage_bytes = b->block_bytes;
+      }
+      CU(cudaMemcpyAsync(b->h_stage, b->res.p, b->block_bytes, cudaMemcpyDeviceToHost, b->stream));
+    } else {
+      RC(batch_fetch_enqueue(b, out));
+    }
+    RC(batch_finish(b));
+    if (staged) {
+      const ResLayout L = res_layout(b->slot, b->k);
+      const uint8_t* h = static_cast<const uint8_t*>(b->h_stage);
+      const uint64_t Q = b->Q, k = b->k;
+      if (out->n_results) std::memcpy(out->n_results, h + L.n, Q * 8);
+      if (out->doc_digest) std::memcpy(out->doc_digest, h + L.dd, Q * 8);
+      if (out->score_digest) std::memcpy(out->score_digest, h + L.sd, Q * 8);
+      if (out->topk_n) std::memcpy(out->topk_n, h + L.tn, Q * 4);
+      if (k && out->topk_doc) std::memcpy(out->topk_doc, h + L.td, Q * k * 4);
+      if (k && out->topk_score) std::memcpy(out->topk_score, h + L.ts, Q * k * 8);
+    }
+    return PB_OK;
   });
 }
 

@@ -126,8 +126,12 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
                                   unsigned long long* __restrict__ s_tiles, unsigned long long* __restrict__ qt_gcount,
                                   uint32_t* __restrict__ qt_q, unsigned long long* __restrict__ q_isg,
                                   unsigned long long* __restrict__ q_grows, unsigned long long* __restrict__ stats,
-                                  UPlan up) {
+                                  UPlan up, uint64_t n_qterms) {
   uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (q == 0) {                // the exclusive scans run over n + 1 entries: give the extra input entry a defined value
+    s_tiles[n_queries] = 0ull; qt_gcount[n_qterms] = 0ull;
+    if (up.q_isu) { up.q_isu[n_queries] = 0ull; up.q_isu2[n_queries] = 0ull; }
+  }
   unsigned long long st_rows = 0, st_live = 0, st_ptr = 0;
   unsigned long long su_rows = 0, su_live = 0, su_ptr = 0;
   if (q < n_queries) {

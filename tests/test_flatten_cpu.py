@@ -155,3 +155,27 @@ def test_synthetic_corpus_matches_oracle_counts():
     a = H.image_arrays(ix.flatten())
     for p in ["a", "ab", "s", "sz", "q"]:
         assert H.image_expand(a, p) == o.expand_term(p)
+
+
+def test_remove_after_flatten_updates_only_the_live_state():
+    """remove_document is lazy (src/index.rs:161-191): the flattened structure stays, the image's removed bitmap /
+    n_live_docs / field averages follow in O(1) — no second O(rows) flatten (round-1 advisory)."""
+    import ctypes as C
+    from probly_search_b200 import Index
+    tok = lambda s: s.split(" ")
+    ix = Index(1)
+    for k, d in enumerate(["a b c", "a b", "c c d", "e"]):
+        ix.add_document([lambda d: [d]], tok, k, d)
+    im0 = ix.flatten()
+    p_blocks = C.addressof(im0.post_blocks.contents)
+    rows0, avg0 = int(im0.n_rows), float(im0.field_avg[0])
+    ix.remove_document(2)
+    im1 = ix.flatten()
+    assert C.addressof(im1.post_blocks.contents) == p_blocks and int(im1.n_rows) == rows0      # same buffers: not re-flattened
+    assert int(im1.n_removed) == 1 and int(im1.n_live_docs) == 3
+    assert (im1.removed_bitmap[0] >> 2) & 1
+    assert float(im1.field_avg[0]) == (3 + 2 + 1) / 3 and avg0 == (3 + 2 + 3 + 1) / 4
+    ix.vacuum()
+    im2 = ix.flatten()
+    assert int(im2.n_removed) == 0 and im2.removed_bitmap[0] == 0 and int(im2.n_docs) == 4    # the ordinal stays, unmasked: it owns no row
+    assert int(im2.n_rows) == rows0 - 2
