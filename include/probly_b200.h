@@ -13,9 +13,13 @@
  * thread-local message is available from pb_last_error().  (The reference panics instead:
  * `unwrap()` at src/query.rs:46,63,70 and the NaN sort at :103.)
  * Threading: a pb_builder needs external exclusion for mutation (mirrors `&mut self`); a
- * pb_index is immutable between pb_index_create / pb_index_set_live_state calls; each
- * pb_batch owns its workspace and stream, so batches on one index may run concurrently
- * from different host threads (mirrors `query(&self, ..)`, src/query.rs:22).
+ * pb_index is immutable between pb_index_create / pb_index_set_live_state / pb_index_set_df_extra
+ * calls, which need the same exclusion against running batches; each pb_batch owns its workspace
+ * and stream, so DIFFERENT pb_batch objects on one index may run concurrently from different host
+ * threads (mirrors `query(&self, ..)`, src/query.rs:22).  The one-call forms pb_query_batch /
+ * pb_query_full / pb_index_expand_term share one internal batch per index and serialise on it.
+ * A staged pb_batch follows pb_index_set_live_state: its BM25 table is rebuilt when the index's
+ * live state changed since it was staged.
  *
  * There is NO CPU fallback: every query entry point fails with PB_ERR_NO_DEVICE when no
  * CUDA device is usable.
@@ -341,6 +345,21 @@ void pb_host_free(void* p);
 
 const char* pb_last_error(void);
 const char* pb_version(void);
+
+/* Layout pins for foreign bindings that mirror these structs by hand (rust/src/lib.rs, capi.py): LP64, natural alignment. */
+#if defined(__cplusplus)
+#define PB_STATIC_ASSERT(c, m) static_assert(c, m)
+#elif defined(__STDC_VERSION__) && __STDC_VERSION__ >= 201112L
+#define PB_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#else
+#define PB_STATIC_ASSERT(c, m)
+#endif
+PB_STATIC_ASSERT(sizeof(pb_index_image) == 248, "pb_index_image layout");
+PB_STATIC_ASSERT(sizeof(pb_query_batch_desc) == 72, "pb_query_batch_desc layout");
+PB_STATIC_ASSERT(sizeof(pb_query_results) == 48, "pb_query_results layout");
+PB_STATIC_ASSERT(sizeof(pb_batch_stats) == 160, "pb_batch_stats layout");
+PB_STATIC_ASSERT(sizeof(pb_builder_info) == 128, "pb_builder_info layout");
+PB_STATIC_ASSERT(sizeof(pb_doc_tokens) == 32, "pb_doc_tokens layout");
 
 #ifdef __cplusplus
 }

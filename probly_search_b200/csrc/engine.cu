@@ -55,7 +55,13 @@ struct DBuf {
     p = nullptr; cap = 0;
     size_t c = n + n / 8 + 64;
     cudaError_t e = cudaMalloc((void**)&p, c * sizeof(T));
-    if (e == cudaSuccess) { cap = c; e = cudaMemset(p, 0, c * sizeof(T)); }     // defined contents: slack and unused slots are copied / scanned
+    if (e == cudaSuccess) {
+      // defined contents (slack and unused slots get copied / scanned).  The fill runs on the default stream while the
+      // batches use non-blocking streams: wait for it, or it could land AFTER an upload into the new buffer.
+      cap = c;
+      e = cudaMemset(p, 0, c * sizeof(T));
+      if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    }
     return e;
   }
   // grow, keeping the first `keep` elements (device-to-device copy on `st`)

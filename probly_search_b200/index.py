@@ -109,6 +109,12 @@ class Index:
         self._ix: Optional[C.c_void_p] = None
         self._image_dirty = True        # structure changed: re-flatten + upload
         self._live_dirty = False        # only the removed set / stats changed
+        self._delta_dirty = False       # documents were added behind the resident image: delta segment
+        self._ix_delta: Optional[C.c_void_p] = None
+        self._n_main_docs = 0           # doc ordinals / posting rows the resident MAIN image covers
+        self._n_main_rows = 0
+        self._sid_main: Optional[np.ndarray] = None     # builder term id of every term ordinal (matches terms across segments)
+        self._sid_delta: Optional[np.ndarray] = None
         self._key_to_id: dict = {}
         self._id_to_key: list = []
         self._ord_to_id: Optional[np.ndarray] = None
@@ -117,7 +123,7 @@ class Index:
     # -- on-disk image (the reference has no serialisation) -----------------------
     def save_image(self, path: str) -> None:
         """Writes the flattened image (what pb_index_create uploads) to `path` (csrc/image_io.cpp)."""
-        im = self.flatten()
+        im = self.flatten()             # always the FULL image (delta segments exist on the device only)
         capi.check(self._L.pb_image_save(C.byref(im), os.fsencode(path)))
 
     @classmethod
@@ -134,7 +140,8 @@ class Index:
         self.device = device
         im = C.cast(self._L.pb_image_file_image(h), C.POINTER(capi.IndexImage)).contents
         self.fields_num = int(im.num_fields)
-        self._image_dirty, self._live_dirty = True, False
+        self._image_dirty, self._live_dirty, self._delta_dirty = True, False, False
+        self._ix_delta, self._n_main_docs, self._n_main_rows, self._sid_main, self._sid_delta = None, 0, 0, None, None
         self._key_to_id, self._id_to_key, self._ord_to_id = {}, [], None
         self._flat_keys = True
         self._batches = weakref.WeakSet()
@@ -184,7 +191,7 @@ class Index:
         fc = np.asarray(fcount, dtype=np.uint32)
         d = capi.DocTokens(buf.ctypes.data, off.ctypes.data, vc.ctypes.data, fc.ctypes.data)
         capi.check(self._L.pb_builder_add_document(self._require_builder(), self._key_id(key), C.byref(d)))
-        self._image_dirty = True
+        self._mark_added()
 
     def add_documents_flat(self, keys: np.ndarray, tok_bytes: np.ndarray, tok_off: np.ndarray,
                            field_tok_count: np.ndarray) -> None:
@@ -195,7 +202,15 @@ class Index:
         self._flat_keys = True
         capi.check(self._L.pb_builder_add_documents(self._require_builder(), len(keys), keys.ctypes.data, tok_bytes.ctypes.data,
                                                     tok_off.ctypes.data, field_tok_count.ctypes.data))
-        self._image_dirty = True
+        self._mark_added()
+
+    def _mark_added(self) -> None:
+        """Documents added behind a resident image become a small DELTA segment at the next query (SURVEY §8f-1:
+        add_document stays cheap, src/index.rs:77-158); without a resident image the next sync flattens everything."""
+        if self._ix is None or self._image_dirty:
+            self._image_dirty = True
+        else:
+            self._delta_dirty = True
 
     def remove_document(self, key: Hashable) -> None:
         """src/index.rs:161-191 — lazy: the postings stay until vacuum()."""
@@ -228,29 +243,111 @@ class Index:
         return self._b
 
     # -- device image --------------------------------------------------------------------------
+    # a delta segment is folded into the main image once it holds more than this share of the main image's rows
+    DELTA_MAX_FRACTION = 0.25
+    DELTA_MIN_ROWS = 1 << 16
+
+    def _term_ids_of_last_flatten(self) -> np.ndarray:
+        n = C.c_uint64(0)
+        self._L.pb_builder_flatten_term_ids(self._b, None, 0, C.byref(n))
+        out = np.zeros(max(int(n.value), 1), dtype=np.uint32)
+        capi.check(self._L.pb_builder_flatten_term_ids(self._b, out.ctypes.data, len(out), C.byref(n)))
+        return out[: int(n.value)]
+
+    def _df_live_of(self, ix, n_terms: int) -> np.ndarray:
+        out = np.zeros(max(n_terms, 1), dtype=np.uint64)
+        capi.check(self._L.pb_index_term_df_live(ix, out.ctypes.data, len(out)))
+        return out[:n_terms]
+
+    def _apply_live_state(self, im) -> None:
+        """Removed set / N / averages of the host index on every resident segment, then each segment learns the other's
+        per-term live counts (BM25's document frequency is over the whole index)."""
+        nd = int(im.n_docs)
+        words = np.ctypeslib.as_array(im.removed_bitmap, shape=((nd + 31) // 32 + 1,))
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:nd]
+        ords = np.ascontiguousarray(np.nonzero(bits)[0], dtype=np.uint32)
+        avg = (C.c_double * 4)(*[im.field_avg[i] for i in range(4)])
+        main_ords = np.ascontiguousarray(ords[ords < self._n_main_docs]) if self._ix_delta is not None else ords
+        capi.check(self._L.pb_index_set_live_state(self._ix, main_ords.ctypes.data, len(main_ords), im.n_live_docs, avg))
+        if self._ix_delta is not None:
+            capi.check(self._L.pb_index_set_live_state(self._ix_delta, ords.ctypes.data, len(ords), im.n_live_docs, avg))
+            dfm = self._df_live_of(self._ix, len(self._sid_main))
+            dfd = self._df_live_of(self._ix_delta, len(self._sid_delta))
+            n_sid = int(max(self._sid_main.max(initial=0), self._sid_delta.max(initial=0))) + 1
+            by_sid_m = np.zeros(n_sid, dtype=np.uint64); by_sid_m[self._sid_main] = dfm
+            by_sid_d = np.zeros(n_sid, dtype=np.uint64); by_sid_d[self._sid_delta] = dfd
+            ex_m = np.ascontiguousarray(by_sid_d[self._sid_main]); ex_d = np.ascontiguousarray(by_sid_m[self._sid_delta])
+            capi.check(self._L.pb_index_set_df_extra(self._ix, ex_m.ctypes.data, len(ex_m)))
+            capi.check(self._L.pb_index_set_df_extra(self._ix_delta, ex_d.ctypes.data, len(ex_d)))
+        else:
+            capi.check(self._L.pb_index_set_df_extra(self._ix, None, 0))
+        self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
+
+    def _drop_delta(self) -> None:
+        if self._ix_delta is not None:
+            self._L.pb_index_destroy(self._ix_delta)
+            self._ix_delta = None
+            self._sid_delta = None
+
+    def compact(self) -> None:
+        """Folds the delta segment into one image (the GPU analogue of a merge; also what vacuum() forces)."""
+        if self._ix_delta is not None or self._delta_dirty:
+            self._image_dirty = True
+        self.sync_device()
+
+    @property
+    def n_segments(self) -> int:
+        return (1 if self._ix is not None else 0) + (1 if self._ix_delta is not None else 0)
+
     def sync_device(self) -> None:
-        """Brings the HBM image up to date with the host index (flatten + upload, or just the
-        removed mask / N / avg when only remove_document happened)."""
-        if self._ix is not None and not self._image_dirty and not self._live_dirty:
+        """Brings the HBM image up to date with the host index: a full flatten + upload the first time and after
+        vacuum(); a small DELTA segment (the rows of the documents added since, under the current trie) after
+        add_document; just the removed mask / N / avg / idf after remove_document."""
+        if self._ix is not None and not self._image_dirty and not self._live_dirty and not self._delta_dirty:
             return
-        im = self.flatten()
+        if getattr(self, "_image_file", None):          # served from a file: one immutable segment
+            im = self.flatten()
+            if self._ix is None:
+                h = C.c_void_p()
+                capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
+                self._ix = h
+                nd = int(im.n_docs)
+                self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
+            self._image_dirty = self._live_dirty = self._delta_dirty = False
+            return
+        if self._ix is not None and not self._image_dirty and self._delta_dirty:
+            info = self.info()
+            delta_rows = int(info.n_rows) - self._n_main_rows
+            if delta_rows > max(self.DELTA_MIN_ROWS, self.DELTA_MAX_FRACTION * self._n_main_rows):
+                self._image_dirty = True                  # the delta has grown: fold it into the main image
         if self._ix is None or self._image_dirty:
+            self._drop_delta()
+            im = self.flatten()
             if self._ix is not None:
                 self._drop_device_index()
             h = C.c_void_p()
             capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
             self._ix = h
-        else:
-            nd = int(im.n_docs)
-            words = np.ctypeslib.as_array(im.removed_bitmap, shape=((nd + 31) // 32 + 1,))
-            bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:nd]
-            ords = np.ascontiguousarray(np.nonzero(bits)[0], dtype=np.uint32)
-            avg = (C.c_double * 4)(*[im.field_avg[i] for i in range(4)])
-            capi.check(self._L.pb_index_set_live_state(self._ix, ords.ctypes.data, len(ords), im.n_live_docs, avg))
-        nd = int(im.n_docs)
-        self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
-        self._image_dirty = False
-        self._live_dirty = False
+            self._n_main_docs, self._n_main_rows = int(im.n_docs), int(im.n_rows)
+            self._sid_main = self._term_ids_of_last_flatten()
+            self._apply_live_state(im)
+        elif self._delta_dirty:
+            im = capi.IndexImage()
+            capi.check(self._L.pb_builder_flatten_from(self._require_builder(), self._n_main_docs, C.byref(im)))
+            self._drop_delta()
+            h = C.c_void_p()
+            capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
+            self._ix_delta = h
+            self._sid_delta = self._term_ids_of_last_flatten()
+            self._apply_live_state(im)
+        else:                                             # only remove_document happened
+            if self._ix_delta is not None:
+                im = capi.IndexImage()
+                capi.check(self._L.pb_builder_flatten_from(self._require_builder(), self._n_main_docs, C.byref(im)))
+            else:
+                im = self.flatten()
+            self._apply_live_state(im)
+        self._image_dirty = self._live_dirty = self._delta_dirty = False
 
     def set_live_state(self, removed_ordinals: np.ndarray, n_live_docs: int, field_avg: Sequence[float]) -> None:
         """pb_index_set_live_state on the resident image: the FULL removed set, the live doc count and the
@@ -275,6 +372,7 @@ class Index:
         later use of them raises instead of touching freed memory."""
         for b in list(getattr(self, "_batches", ())):
             b._invalidate()
+        self._drop_delta()
         self._L.pb_index_destroy(self._ix)
         self._ix = None
 
@@ -292,7 +390,7 @@ class Index:
     # -- queries -------------------------------------------------------------------------------
     def expand_term(self, term: str) -> List[str]:
         """src/query.rs:109-126 (private there; exposed for the expansion-order goldens)."""
-        self.sync_device()
+        self.compact()
         tb = np.frombuffer(term.encode("utf-8") + b"\0", dtype=np.uint8)
         n, need = C.c_uint64(0), C.c_uint64(0)
         capi.check(self._L.pb_index_expand_term(self._ix, tb.ctypes.data, len(tb) - 1, None, 0, C.byref(n), C.byref(need)))
@@ -303,23 +401,33 @@ class Index:
                                                 C.byref(n), C.byref(need)))
         return bytes(out[: need.value]).decode("utf-8").split("\n")
 
+    def _segments(self):
+        return [h for h in (self._ix, self._ix_delta) if h is not None]
+
     def query_full_flat(self, fq: FlatQueries, score_calculator, fields_boost: Sequence[float],
                         cap: Optional[int] = None):
-        """Full result sets of every query of the batch: arrays (query, doc ordinal, score), unordered."""
+        """Full result sets of every query of the batch: arrays (query, doc ordinal, score), unordered.  With a delta
+        segment the sets of the two segments are concatenated: a document lives in exactly one of them."""
         self.sync_device()
         d, _keep = self._desc(fq, score_calculator, fields_boost, 0)
-        cap = int(cap if cap is not None else max(1024, fq.n_queries * 64))
-        while True:
-            oq = np.zeros(cap, dtype=np.uint32)
-            od = np.zeros(cap, dtype=np.uint32)
-            os_ = np.zeros(cap, dtype=np.float64)
-            n = C.c_uint64(0)
-            rc = self._L.pb_query_full(self._ix, C.byref(d), cap, oq.ctypes.data, od.ctypes.data, os_.ctypes.data, C.byref(n))
-            if rc == capi.PB_ERR_CAPACITY:
-                cap = int(n.value) + 16
-                continue
-            capi.check(rc)
-            return oq[: n.value], od[: n.value], os_[: n.value]
+        parts = []
+        for ix in self._segments():
+            c = int(cap if cap is not None else max(1024, fq.n_queries * 64))
+            while True:
+                oq = np.zeros(c, dtype=np.uint32)
+                od = np.zeros(c, dtype=np.uint32)
+                os_ = np.zeros(c, dtype=np.float64)
+                n = C.c_uint64(0)
+                rc = self._L.pb_query_full(ix, C.byref(d), c, oq.ctypes.data, od.ctypes.data, os_.ctypes.data, C.byref(n))
+                if rc == capi.PB_ERR_CAPACITY:
+                    c = int(n.value) + 16
+                    continue
+                capi.check(rc)
+                parts.append((oq[: n.value], od[: n.value], os_[: n.value]))
+                break
+        if len(parts) == 1:
+            return parts[0]
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
 
     def query(self, query: str, score_calculator, tokenizer: Tokenizer, fields_boost: Sequence[float]) -> List[QueryResult]:
         """src/query.rs:21-106.  Result order: score descending; exactly tied scores by document
@@ -330,13 +438,37 @@ class Index:
         return [QueryResult(self._key_of_ord(int(docs[i])), float(scores[i])) for i in order]
 
     def query_batch_flat(self, fq: FlatQueries, score_calculator, fields_boost: Sequence[float], top_k: int = 10) -> BatchResults:
-        """pb_query_batch: host buffers in, host buffers out."""
+        """pb_query_batch: host buffers in, host buffers out.  With a delta segment both segments answer the batch
+        and the per-query results are merged: counts and digests add (disjoint doc sets), the top-k lists merge by
+        (score desc, doc ordinal asc)."""
         self.sync_device()
         d, _keep = self._desc(fq, score_calculator, fields_boost, top_k)
-        res = BatchResults(fq.n_queries, top_k)
-        rs = res.c_struct()
-        capi.check(self._L.pb_query_batch(self._ix, C.byref(d), C.byref(rs)))
-        return res
+        outs = []
+        for ix in self._segments():
+            res = BatchResults(fq.n_queries, top_k)
+            rs = res.c_struct()
+            capi.check(self._L.pb_query_batch(ix, C.byref(d), C.byref(rs)))
+            outs.append(res)
+        if len(outs) == 1:
+            return outs[0]
+        a, b = outs
+        m = BatchResults(fq.n_queries, top_k)
+        m.n_results[:] = a.n_results + b.n_results
+        m.doc_digest[:] = a.doc_digest + b.doc_digest            # wrap-around sums (include/probly_b200.h "Digests")
+        m.score_digest[:] = a.score_digest + b.score_digest
+        if top_k:
+            k = top_k
+            sc = np.concatenate([a.topk_score, b.topk_score], axis=1)
+            dc = np.concatenate([a.topk_doc, b.topk_doc], axis=1)
+            valid = np.concatenate([np.arange(k)[None, :] < a.topk_n[:, None], np.arange(k)[None, :] < b.topk_n[:, None]], axis=1)
+            sc_key = np.where(valid, sc, -np.inf)
+            order = np.lexsort((dc, -sc_key), axis=1)[:, :k]       # per query: score desc, doc asc; invalid slots last
+            rows = np.arange(fq.n_queries)[:, None]
+            m.topk_n[:] = np.minimum(a.topk_n.astype(np.uint64) + b.topk_n, k).astype(np.uint32)
+            keep = np.arange(k)[None, :] < m.topk_n[:, None]
+            m.topk_score[:] = np.where(keep, sc[rows, order], 0.0)
+            m.topk_doc[:] = np.where(keep, dc[rows, order], 0)
+        return m
 
     def query_batch(self, queries: Sequence[str], score_calculator, tokenizer: Tokenizer,
                     fields_boost: Sequence[float], top_k: int = 10) -> List[List[QueryResult]]:
@@ -356,14 +488,14 @@ class Index:
 
     def device_layout(self) -> dict:
         """How the posting columns are held in HBM (pb_device_layout): narrow u16 codes or u32 columns."""
-        self.sync_device()
+        self.compact()
         d = capi.DeviceLayout()
         capi.check(self._L.pb_index_device_layout(self._ix, C.byref(d)))
         return {"narrow": bool(d.narrow), "bytes_per_row": int(d.bytes_per_row), "posting_bytes": int(d.posting_bytes),
                 "fl_bits": [int(x) for x in d.fl_bits][: self.fields_num]}
 
     def term_df_live(self) -> np.ndarray:
-        self.sync_device()
+        self.compact()
         im = self.flatten()
         out = np.zeros(max(int(im.n_terms), 1), dtype=np.uint64)
         capi.check(self._L.pb_index_term_df_live(self._ix, out.ctypes.data, len(out)))
@@ -376,7 +508,7 @@ class DeviceBatch:
     ncclAllGather of the packed result block on the batch's stream (multi-GPU)."""
 
     def __init__(self, index: Index, fq: FlatQueries, score_calculator, fields_boost: Sequence[float], top_k: int = 10):
-        index.sync_device()
+        index.compact()                  # a staged batch runs on ONE image: a pending delta segment is folded in first
         self._L = index._L
         self.index = index
         self.fq = fq
@@ -412,11 +544,22 @@ class DeviceBatch:
         self._comm = comm
         self._slot = int(slot_queries)
 
+    def _fresh(self):
+        """A staged batch answers from the image it was staged on: removals follow (live state only), added
+        documents need a new batch (the delta segment is a second image)."""
+        ix = self.index
+        if ix._image_dirty or ix._delta_dirty or ix._ix_delta is not None:
+            raise capi.ProblyError(capi.PB_ERR_INVALID, "documents were added to the index after this DeviceBatch was staged; "
+                                   "stage a new one (Index.compact() folds the delta segment in)")
+        if ix._live_dirty:
+            ix.sync_device()
+        return self._handle()
+
     def run(self) -> None:
-        capi.check(self._L.pb_batch_run(self._handle()))
+        capi.check(self._L.pb_batch_run(self._fresh()))
 
     def run_local(self) -> None:
-        capi.check(self._L.pb_batch_run_local(self._handle()))
+        capi.check(self._L.pb_batch_run_local(self._fresh()))
 
     def fetch(self) -> BatchResults:
         res = BatchResults(self.fq.n_queries, self.top_k)

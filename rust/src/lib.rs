@@ -39,7 +39,9 @@ struct PbDocTokens {
 }
 #[repr(C)]
 struct PbIndexImage {
-    _opaque: [u8; 256], // filled by pb_builder_flatten, passed straight to pb_index_create
+    // filled by pb_builder_flatten, passed straight to pb_index_create.  248 bytes, 8-aligned: pinned by
+    // PB_STATIC_ASSERT(sizeof(pb_index_image) == 248) in include/probly_b200.h (use bindgen in a real build).
+    _opaque: [u64; 31],
 }
 #[repr(C)]
 struct PbQueryBatchDesc {
@@ -66,6 +68,8 @@ struct PbQueryResults {
 #[repr(C)] struct PbBuilder { _p: [u8; 0] }
 #[repr(C)] struct PbIndex { _p: [u8; 0] }
 #[repr(C)] struct PbImageFile { _p: [u8; 0] }
+#[repr(C)] struct PbComm { _p: [u8; 0] }
+#[repr(C)] struct PbGroup { _p: [u8; 0] }
 
 extern "C" {
     fn pb_builder_create(num_fields: u32, out: *mut *mut PbBuilder) -> c_int;
@@ -76,6 +80,18 @@ extern "C" {
     fn pb_builder_flatten(b: *mut PbBuilder, out: *mut PbIndexImage) -> c_int;
     fn pb_index_create(image: *const PbIndexImage, device: c_int, out: *mut *mut PbIndex) -> c_int;
     fn pb_index_destroy(ix: *mut PbIndex);
+    // incremental maintenance: a delta segment = the rows of the docs added since `from_doc_ordinal` under the
+    // current trie; each segment is told the other's per-term live counts (BM25 df is over the whole index)
+    fn pb_builder_flatten_from(b: *mut PbBuilder, from_doc_ordinal: u64, out: *mut PbIndexImage) -> c_int;
+    fn pb_builder_flatten_term_ids(b: *const PbBuilder, out: *mut u32, cap: u64, n_terms: *mut u64) -> c_int;
+    fn pb_index_set_df_extra(ix: *mut PbIndex, df_extra: *const u64, n: u64) -> c_int;
+    // multi-GPU: one process per GPU (pb_comm + pb_batch_set_gather) or one process, several devices (pb_group)
+    fn pb_comm_unique_id(id: *mut u8) -> c_int; // [128]
+    fn pb_comm_create(id: *const u8, rank: c_int, world: c_int, device: c_int, out: *mut *mut PbComm) -> c_int;
+    fn pb_comm_destroy(c: *mut PbComm);
+    fn pb_group_create(image: *const PbIndexImage, devices: *const c_int, n: c_int, out: *mut *mut PbGroup) -> c_int;
+    fn pb_group_query_batch(g: *mut PbGroup, q: *const PbQueryBatchDesc, out: *mut PbQueryResults) -> c_int;
+    fn pb_group_destroy(g: *mut PbGroup);
     // on-disk image (the reference has no serialisation): save what `flatten` produced, serve from a file
     fn pb_image_save(image: *const PbIndexImage, path: *const c_char) -> c_int;
     fn pb_image_load(path: *const c_char, out: *mut *mut PbImageFile) -> c_int;
