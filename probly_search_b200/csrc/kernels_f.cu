@@ -1,5 +1,9 @@
 // The per-field-count kernels (kernels.cuh) for ONE field count: compiled four times with
 // -DPB_F=1..4 so that the 8 instantiations of the scoring kernel per F build in parallel.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "field_ops.hpp"
 
 #ifndef PB_F
@@ -11,9 +15,26 @@ namespace {
 
 constexpr int F = PB_F;
 
+// The dynamic shared-memory limit of a kernel is per device and only ever RAISED here: indexes with different table
+// sizes (a main image and its delta segment, say) launch the same instantiation, and the callers cache the occupancy.
+template <class K>
+cudaError_t raise_smem_limit(K kernel, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> limit;      // (kernel, device) -> limit set so far
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  int& cur = limit[{reinterpret_cast<const void*>(kernel), dev}];
+  if ((int)smem <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) cur = (int)smem;
+  return e;
+}
+
 template <int SC, bool G, bool N>
 cudaError_t occ_t(int* per_sm, int threads, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(score_kernel<F, SC, G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = raise_smem_limit(score_kernel<F, SC, G, N>, smem);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, score_kernel<F, SC, G, N>, threads, smem);
 }
@@ -64,7 +85,7 @@ cudaError_t live_df_launch(const IndexView* ix, unsigned long long* df_live, uin
 
 template <bool GEN>
 cudaError_t union_occ_t(int* per_sm, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(union_kernel<F, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = raise_smem_limit(union_kernel<F, GEN>, smem);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, union_kernel<F, GEN>, UShape<GEN>::THREADS, smem);
 }
