@@ -179,6 +179,15 @@ int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t
 /* Segmented index: live occurrence counts of every term of THIS image in the other segments ([n_terms], by term
  * ordinal; n = 0 clears).  BM25's idf (bm25.rs:41-56) is recomputed from local + extra counts. */
 int pb_index_set_df_extra(pb_index* ix, const uint64_t* df_extra, uint64_t n);
+/* The whole arrangement in one call: `delta` (a pb_index created from a pb_builder_flatten_from image of the same
+ * builder, same device) becomes the delta segment of `ix`, which takes ownership (delta = NULL detaches and destroys it).
+ * The term id arrays are pb_builder_flatten_term_ids of the two flattens.  From then on
+ *   pb_query_batch / pb_query_full on `ix` answer for BOTH segments (counts and digests add, top-k lists merge);
+ *   pb_index_set_live_state on `ix` takes the removed ordinals of the WHOLE index and keeps both segments and the
+ *     document frequencies they exchange up to date;
+ *   pb_batch_create / pb_index_expand_term refuse (PB_ERR_UNSUPPORTED): a staged batch runs on one image. */
+int pb_index_attach_delta(pb_index* ix, pb_index* delta, const uint32_t* main_term_ids, uint64_t n_main_terms,
+                          const uint32_t* delta_term_ids, uint64_t n_delta_terms);
 void pb_index_destroy(pb_index* ix);
 /* expand_term (query.rs:109-126) through the device descent kernel: the expansions of `term`
  * joined by '\n' into out (cap bytes).  *n_expansions / *needed are always set. */

@@ -142,6 +142,9 @@ struct pb_index {
   uint64_t live_epoch = 0;       // bumped by every pb_index_set_live_state: staged batches rebuild their BM25 table
   std::mutex occ_mu;             // guards occ_cache
   std::map<uint64_t, int> occ_cache;   // resident CTAs per SM of a scoring-kernel shape
+  // delta segment (pb_index_attach_delta): the rows of the documents added behind this image, under the current trie
+  pb_index* delta = nullptr;     // owned
+  std::vector<uint32_t> sid;     // builder term id of every term ordinal of THIS image (matches terms across the segments)
   std::mutex mu;                 // guards `scratch`
   pb_batch* scratch = nullptr;   // reused by pb_query_batch / pb_query_full / expand_term
 
@@ -1159,6 +1162,27 @@ int index_scratch(pb_index* ix, pb_batch** out) {
 
 }  // namespace
 
+// Each segment learns the other's per-term live occurrence counts (matched by the builder's stable term ids) and
+// recomputes its idf: the reference has ONE posting list per term, so BM25's document frequency is the sum.
+static int segments_exchange_df(pb_index* m) {
+  pb_index* d = m->delta;
+  if (!d) { m->h_df_extra.clear(); return index_upload_idf(m); }
+  uint32_t n_sid = 0;
+  for (uint32_t v : m->sid) n_sid = std::max(n_sid, v + 1);
+  for (uint32_t v : d->sid) n_sid = std::max(n_sid, v + 1);
+  std::vector<uint64_t> by_m(n_sid, 0), by_d(n_sid, 0);
+  for (size_t t = 0; t < m->sid.size(); ++t) by_m[m->sid[t]] = m->h_df_live[t];
+  for (size_t t = 0; t < d->sid.size(); ++t) by_d[d->sid[t]] = d->h_df_live[t];
+  m->h_df_extra.resize(m->sid.size());
+  d->h_df_extra.resize(d->sid.size());
+  for (size_t t = 0; t < m->sid.size(); ++t) m->h_df_extra[t] = by_d[m->sid[t]];
+  for (size_t t = 0; t < d->sid.size(); ++t) d->h_df_extra[t] = by_m[d->sid[t]];
+  ++m->live_epoch; ++d->live_epoch;
+  CU(cudaSetDevice(m->device));
+  RC(index_upload_idf(m));
+  return index_upload_idf(d);
+}
+
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -1286,15 +1310,29 @@ int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t
   if (!ix || !field_avg || (n_removed && !removed_ords)) { pb::set_error("pb_index_set_live_state: null argument"); return PB_ERR_INVALID; }
   PB_TRY({
     std::lock_guard<std::mutex> lk(ix->mu);
-    std::vector<uint32_t> bm((ix->n_docs + 31) / 32 + 1, 0);
-    uint64_t distinct = 0;
+    // with a delta segment the ordinals are those of the whole index: the main image takes the ones it covers
+    const uint64_t n_all = ix->delta ? ix->delta->n_docs : ix->n_docs;
+    std::vector<uint32_t> bm((ix->n_docs + 31) / 32 + 1, 0), bmd;
+    if (ix->delta) bmd.assign((n_all + 31) / 32 + 1, 0);
+    uint64_t distinct = 0, distinct_d = 0;
     for (uint64_t i = 0; i < n_removed; ++i) {
       uint32_t d = removed_ords[i];
-      if (d >= ix->n_docs) { pb::set_error("pb_index_set_live_state: ordinal %u out of range", d); return PB_ERR_INVALID; }
-      if (!((bm[d >> 5] >> (d & 31)) & 1u)) ++distinct;
-      bm[d >> 5] |= 1u << (d & 31);
+      if (d >= n_all) { pb::set_error("pb_index_set_live_state: ordinal %u out of range", d); return PB_ERR_INVALID; }
+      if (ix->delta) {
+        if (!((bmd[d >> 5] >> (d & 31)) & 1u)) ++distinct_d;
+        bmd[d >> 5] |= 1u << (d & 31);
+      }
+      if (d < ix->n_docs) {
+        if (!((bm[d >> 5] >> (d & 31)) & 1u)) ++distinct;
+        bm[d >> 5] |= 1u << (d & 31);
+      }
     }
-    return index_apply_live_state(ix, bm.data(), distinct, n_live_docs, field_avg);
+    RC(index_apply_live_state(ix, bm.data(), distinct, n_live_docs, field_avg));
+    if (ix->delta) {
+      RC(index_apply_live_state(ix->delta, bmd.data(), distinct_d, n_live_docs, field_avg));
+      RC(segments_exchange_df(ix));
+    }
+    return PB_OK;
   });
 }
 
@@ -1310,9 +1348,35 @@ int pb_index_set_df_extra(pb_index* ix, const uint64_t* df_extra, uint64_t n) {
   });
 }
 
+int pb_index_attach_delta(pb_index* ix, pb_index* delta, const uint32_t* main_term_ids, uint64_t n_main_terms,
+                          const uint32_t* delta_term_ids, uint64_t n_delta_terms) {
+  if (!ix) { pb::set_error("pb_index_attach_delta: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (delta) {
+      if (delta == ix || delta->delta) { pb::set_error("pb_index_attach_delta: a delta segment cannot have one of its own"); return PB_ERR_INVALID; }
+      if (delta->device != ix->device || delta->F != ix->F) { pb::set_error("pb_index_attach_delta: the segments must live on one device and have the same fields"); return PB_ERR_INVALID; }
+      if (n_main_terms != ix->n_terms || n_delta_terms != delta->n_terms || (n_main_terms && !main_term_ids) || (n_delta_terms && !delta_term_ids)) {
+        pb::set_error("pb_index_attach_delta: term id arrays must have one entry per term of each image"); return PB_ERR_INVALID;
+      }
+      if (delta->n_docs < ix->n_docs) { pb::set_error("pb_index_attach_delta: the delta image must cover the whole ordinal range"); return PB_ERR_INVALID; }
+    }
+    if (ix->delta && ix->delta != delta) pb_index_destroy(ix->delta);
+    ix->delta = delta;
+    if (delta) {
+      ix->sid.assign(main_term_ids, main_term_ids + n_main_terms);
+      delta->sid.assign(delta_term_ids, delta_term_ids + n_delta_terms);
+    } else {
+      ix->sid.clear();
+    }
+    return segments_exchange_df(ix);
+  });
+}
+
 void pb_index_destroy(pb_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
+  if (ix->delta) pb_index_destroy(ix->delta);
   delete ix->scratch;
   delete ix;
 }
@@ -1385,6 +1449,7 @@ int pb_index_device_layout(pb_index* ix, pb_device_layout* out) {
 int pb_index_expand_term(pb_index* ix, const uint8_t* term, uint64_t term_len, uint8_t* out, uint64_t cap,
                          uint64_t* n_expansions, uint64_t* needed) {
   if (!ix || !n_expansions || !needed || (term_len && !term)) { pb::set_error("pb_index_expand_term: null argument"); return PB_ERR_INVALID; }
+  if (ix->delta) { pb::set_error("pb_index_expand_term: the index has a delta segment (fold it in first)"); return PB_ERR_UNSUPPORTED; }
   PB_TRY({
     std::lock_guard<std::mutex> lk(ix->mu);
     *n_expansions = 0; *needed = 0;
@@ -1430,6 +1495,7 @@ int pb_index_expand_term(pb_index* ix, const uint8_t* term, uint64_t term_len, u
 
 int pb_batch_create(pb_index* ix, const pb_query_batch_desc* q, pb_batch** out) {
   if (!ix || !q || !out) { pb::set_error("pb_batch_create: null argument"); return PB_ERR_INVALID; }
+  if (ix->delta) { pb::set_error("pb_batch_create: the index has a delta segment; a staged batch runs on one image (fold the delta in, or use pb_query_batch)"); return PB_ERR_UNSUPPORTED; }
   PB_TRY({
     pb_batch* b = nullptr;
     RC(batch_new(ix, &b));
@@ -1550,8 +1616,7 @@ int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out) {
   return PB_OK;
 }
 
-int pb_query_batch(pb_index* ix, const pb_query_batch_desc* q, pb_query_results* out) {
-  if (!ix || !q || !out) { pb::set_error("pb_query_batch: null argument"); return PB_ERR_INVALID; }
+static int query_batch_one(pb_index* ix, const pb_query_batch_desc* q, pb_query_results* out) {
   PB_TRY({
     std::lock_guard<std::mutex> lk(ix->mu);
     pb_batch* b = nullptr;
@@ -1590,15 +1655,55 @@ int pb_query_batch(pb_index* ix, const pb_query_batch_desc* q, pb_query_results*
   });
 }
 
+int pb_query_batch(pb_index* ix, const pb_query_batch_desc* q, pb_query_results* out) {
+  if (!ix || !q || !out) { pb::set_error("pb_query_batch: null argument"); return PB_ERR_INVALID; }
+  if (!ix->delta) return query_batch_one(ix, q, out);
+  // Segmented index: both segments answer the batch; a document lives in exactly one of them, so counts and digests
+  // add and the two (score desc, doc asc) top-k lists merge.
+  PB_TRY({
+    const uint64_t Q = q->n_queries, k = q->top_k, kk = std::max<uint64_t>(k, 1);
+    std::vector<uint64_t> n[2], dd[2], sd[2];
+    std::vector<uint32_t> tn[2], td[2];
+    std::vector<double> ts[2];
+    pb_index* seg[2] = {ix, ix->delta};
+    for (int s2 = 0; s2 < 2; ++s2) {
+      n[s2].assign(Q + 1, 0); dd[s2].assign(Q + 1, 0); sd[s2].assign(Q + 1, 0); tn[s2].assign(Q + 1, 0);
+      td[s2].assign(Q * kk + 1, 0); ts[s2].assign(Q * kk + 1, 0.0);
+      pb_query_results r = {n[s2].data(), dd[s2].data(), sd[s2].data(), tn[s2].data(), td[s2].data(), ts[s2].data()};
+      RC(query_batch_one(seg[s2], q, &r));
+    }
+    for (uint64_t i = 0; i < Q; ++i) {
+      if (out->n_results) out->n_results[i] = n[0][i] + n[1][i];
+      if (out->doc_digest) out->doc_digest[i] = dd[0][i] + dd[1][i];
+      if (out->score_digest) out->score_digest[i] = sd[0][i] + sd[1][i];
+      uint32_t a = 0, b2 = 0, m = 0;
+      const uint32_t na = tn[0][i], nb = tn[1][i];
+      while (m < k && (a < na || b2 < nb)) {
+        bool take_a = b2 >= nb;
+        if (a < na && b2 < nb) {
+          const double sa = ts[0][i * kk + a], sb = ts[1][i * kk + b2];
+          take_a = sa > sb || (sa == sb && td[0][i * kk + a] < td[1][i * kk + b2]);
+        }
+        const int s2 = take_a ? 0 : 1;
+        const uint64_t src = i * kk + (take_a ? a++ : b2++);
+        if (out->topk_doc) out->topk_doc[i * k + m] = td[s2][src];
+        if (out->topk_score) out->topk_score[i * k + m] = ts[s2][src];
+        ++m;
+      }
+      if (out->topk_n) out->topk_n[i] = m;
+    }
+    return PB_OK;
+  });
+}
+
 int pb_index_last_stats(pb_index* ix, pb_batch_stats* out) {
   if (!ix || !out || !ix->scratch) return PB_ERR_INVALID;
   *out = ix->scratch->st;
   return PB_OK;
 }
 
-int pb_query_full(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint32_t* out_query, uint32_t* out_doc,
-                  double* out_score, uint64_t* n_total) {
-  if (!ix || !q || !n_total) { pb::set_error("pb_query_full: null argument"); return PB_ERR_INVALID; }
+static int query_full_one(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint32_t* out_query, uint32_t* out_doc,
+                          double* out_score, uint64_t* n_total) {
   PB_TRY({
     std::lock_guard<std::mutex> lk(ix->mu);
     pb_batch* b = nullptr;
@@ -1620,6 +1725,26 @@ int pb_query_full(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint
     }
     return PB_OK;
   });
+}
+
+int pb_query_full(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint32_t* out_query, uint32_t* out_doc,
+                  double* out_score, uint64_t* n_total) {
+  if (!ix || !q || !n_total) { pb::set_error("pb_query_full: null argument"); return PB_ERR_INVALID; }
+  if (!ix->delta) return query_full_one(ix, q, cap, out_query, out_doc, out_score, n_total);
+  // segmented index: the result sets of the two segments are disjoint by document: concatenated
+  uint64_t n0 = 0, n1 = 0;
+  int rc0 = query_full_one(ix, q, cap, out_query, out_doc, out_score, &n0);
+  if (rc0 != PB_OK && rc0 != PB_ERR_CAPACITY) return rc0;
+  const uint64_t used = rc0 == PB_OK ? n0 : cap;
+  int rc1 = query_full_one(ix->delta, q, cap - used, out_query ? out_query + used : nullptr, out_doc ? out_doc + used : nullptr,
+                           out_score ? out_score + used : nullptr, &n1);
+  if (rc1 != PB_OK && rc1 != PB_ERR_CAPACITY) return rc1;
+  *n_total = n0 + n1;
+  if (rc0 == PB_ERR_CAPACITY || rc1 == PB_ERR_CAPACITY) {
+    pb::set_error("pb_query_full: %llu results, capacity %llu", (ull)(n0 + n1), (ull)cap);
+    return PB_ERR_CAPACITY;
+  }
+  return PB_OK;
 }
 
 void* pb_host_alloc(size_t bytes) {

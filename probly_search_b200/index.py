@@ -254,38 +254,22 @@ class Index:
         capi.check(self._L.pb_builder_flatten_term_ids(self._b, out.ctypes.data, len(out), C.byref(n)))
         return out[: int(n.value)]
 
-    def _df_live_of(self, ix, n_terms: int) -> np.ndarray:
-        out = np.zeros(max(n_terms, 1), dtype=np.uint64)
-        capi.check(self._L.pb_index_term_df_live(ix, out.ctypes.data, len(out)))
-        return out[:n_terms]
-
     def _apply_live_state(self, im) -> None:
-        """Removed set / N / averages of the host index on every resident segment, then each segment learns the other's
-        per-term live counts (BM25's document frequency is over the whole index)."""
+        """Removed set / N / averages of the host index on the resident image.  With a delta segment attached the
+        library splits the removed ordinals over the two segments and lets them exchange their per-term live counts
+        (BM25's document frequency is over the whole index)."""
         nd = int(im.n_docs)
         words = np.ctypeslib.as_array(im.removed_bitmap, shape=((nd + 31) // 32 + 1,))
         bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:nd]
         ords = np.ascontiguousarray(np.nonzero(bits)[0], dtype=np.uint32)
         avg = (C.c_double * 4)(*[im.field_avg[i] for i in range(4)])
-        main_ords = np.ascontiguousarray(ords[ords < self._n_main_docs]) if self._ix_delta is not None else ords
-        capi.check(self._L.pb_index_set_live_state(self._ix, main_ords.ctypes.data, len(main_ords), im.n_live_docs, avg))
-        if self._ix_delta is not None:
-            capi.check(self._L.pb_index_set_live_state(self._ix_delta, ords.ctypes.data, len(ords), im.n_live_docs, avg))
-            dfm = self._df_live_of(self._ix, len(self._sid_main))
-            dfd = self._df_live_of(self._ix_delta, len(self._sid_delta))
-            n_sid = int(max(self._sid_main.max(initial=0), self._sid_delta.max(initial=0))) + 1
-            by_sid_m = np.zeros(n_sid, dtype=np.uint64); by_sid_m[self._sid_main] = dfm
-            by_sid_d = np.zeros(n_sid, dtype=np.uint64); by_sid_d[self._sid_delta] = dfd
-            ex_m = np.ascontiguousarray(by_sid_d[self._sid_main]); ex_d = np.ascontiguousarray(by_sid_m[self._sid_delta])
-            capi.check(self._L.pb_index_set_df_extra(self._ix, ex_m.ctypes.data, len(ex_m)))
-            capi.check(self._L.pb_index_set_df_extra(self._ix_delta, ex_d.ctypes.data, len(ex_d)))
-        else:
-            capi.check(self._L.pb_index_set_df_extra(self._ix, None, 0))
+        capi.check(self._L.pb_index_set_live_state(self._ix, ords.ctypes.data, len(ords), im.n_live_docs, avg))
         self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
 
     def _drop_delta(self) -> None:
         if self._ix_delta is not None:
-            self._L.pb_index_destroy(self._ix_delta)
+            if self._ix is not None:                   # the main image owns its delta segment: detaching destroys it
+                capi.check(self._L.pb_index_attach_delta(self._ix, None, None, 0, None, 0))
             self._ix_delta = None
             self._sid_delta = None
 
@@ -334,11 +318,17 @@ class Index:
         elif self._delta_dirty:
             im = capi.IndexImage()
             capi.check(self._L.pb_builder_flatten_from(self._require_builder(), self._n_main_docs, C.byref(im)))
-            self._drop_delta()
             h = C.c_void_p()
             capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
-            self._ix_delta = h
             self._sid_delta = self._term_ids_of_last_flatten()
+            # pb_index_attach_delta: the main image takes ownership (a previous delta is destroyed), the two segments
+            # exchange their per-term live counts, and the query entry points answer for both from now on
+            rc = self._L.pb_index_attach_delta(self._ix, h, self._sid_main.ctypes.data, len(self._sid_main),
+                                               self._sid_delta.ctypes.data, len(self._sid_delta))
+            if rc != capi.PB_OK:
+                self._L.pb_index_destroy(h)
+                capi.check(rc)
+            self._ix_delta = h
             self._apply_live_state(im)
         else:                                             # only remove_document happened
             if self._ix_delta is not None:
@@ -372,9 +362,10 @@ class Index:
         later use of them raises instead of touching freed memory."""
         for b in list(getattr(self, "_batches", ())):
             b._invalidate()
-        self._drop_delta()
-        self._L.pb_index_destroy(self._ix)
+        self._L.pb_index_destroy(self._ix)      # destroys an attached delta segment with it
         self._ix = None
+        self._ix_delta = None
+        self._sid_delta = None
 
     def _key_of_ord(self, o: int):
         kid = int(self._ord_to_id[o])
@@ -401,33 +392,24 @@ class Index:
                                                 C.byref(n), C.byref(need)))
         return bytes(out[: need.value]).decode("utf-8").split("\n")
 
-    def _segments(self):
-        return [h for h in (self._ix, self._ix_delta) if h is not None]
-
     def query_full_flat(self, fq: FlatQueries, score_calculator, fields_boost: Sequence[float],
                         cap: Optional[int] = None):
-        """Full result sets of every query of the batch: arrays (query, doc ordinal, score), unordered.  With a delta
-        segment the sets of the two segments are concatenated: a document lives in exactly one of them."""
+        """Full result sets of every query of the batch: arrays (query, doc ordinal, score), unordered (with a delta
+        segment attached the library concatenates the two segments' sets: a document lives in exactly one)."""
         self.sync_device()
         d, _keep = self._desc(fq, score_calculator, fields_boost, 0)
-        parts = []
-        for ix in self._segments():
-            c = int(cap if cap is not None else max(1024, fq.n_queries * 64))
-            while True:
-                oq = np.zeros(c, dtype=np.uint32)
-                od = np.zeros(c, dtype=np.uint32)
-                os_ = np.zeros(c, dtype=np.float64)
-                n = C.c_uint64(0)
-                rc = self._L.pb_query_full(ix, C.byref(d), c, oq.ctypes.data, od.ctypes.data, os_.ctypes.data, C.byref(n))
-                if rc == capi.PB_ERR_CAPACITY:
-                    c = int(n.value) + 16
-                    continue
-                capi.check(rc)
-                parts.append((oq[: n.value], od[: n.value], os_[: n.value]))
-                break
-        if len(parts) == 1:
-            return parts[0]
-        return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+        cap = int(cap if cap is not None else max(1024, fq.n_queries * 64))
+        while True:
+            oq = np.zeros(cap, dtype=np.uint32)
+            od = np.zeros(cap, dtype=np.uint32)
+            os_ = np.zeros(cap, dtype=np.float64)
+            n = C.c_uint64(0)
+            rc = self._L.pb_query_full(self._ix, C.byref(d), cap, oq.ctypes.data, od.ctypes.data, os_.ctypes.data, C.byref(n))
+            if rc == capi.PB_ERR_CAPACITY:
+                cap = int(n.value) + 16
+                continue
+            capi.check(rc)
+            return oq[: n.value], od[: n.value], os_[: n.value]
 
     def query(self, query: str, score_calculator, tokenizer: Tokenizer, fields_boost: Sequence[float]) -> List[QueryResult]:
         """src/query.rs:21-106.  Result order: score descending; exactly tied scores by document
@@ -438,37 +420,13 @@ class Index:
         return [QueryResult(self._key_of_ord(int(docs[i])), float(scores[i])) for i in order]
 
     def query_batch_flat(self, fq: FlatQueries, score_calculator, fields_boost: Sequence[float], top_k: int = 10) -> BatchResults:
-        """pb_query_batch: host buffers in, host buffers out.  With a delta segment both segments answer the batch
-        and the per-query results are merged: counts and digests add (disjoint doc sets), the top-k lists merge by
-        (score desc, doc ordinal asc)."""
+        """pb_query_batch: host buffers in, host buffers out (both segments answer when a delta is attached)."""
         self.sync_device()
         d, _keep = self._desc(fq, score_calculator, fields_boost, top_k)
-        outs = []
-        for ix in self._segments():
-            res = BatchResults(fq.n_queries, top_k)
-            rs = res.c_struct()
-            capi.check(self._L.pb_query_batch(ix, C.byref(d), C.byref(rs)))
-            outs.append(res)
-        if len(outs) == 1:
-            return outs[0]
-        a, b = outs
-        m = BatchResults(fq.n_queries, top_k)
-        m.n_results[:] = a.n_results + b.n_results
-        m.doc_digest[:] = a.doc_digest + b.doc_digest            # wrap-around sums (include/probly_b200.h "Digests")
-        m.score_digest[:] = a.score_digest + b.score_digest
-        if top_k:
-            k = top_k
-            sc = np.concatenate([a.topk_score, b.topk_score], axis=1)
-            dc = np.concatenate([a.topk_doc, b.topk_doc], axis=1)
-            valid = np.concatenate([np.arange(k)[None, :] < a.topk_n[:, None], np.arange(k)[None, :] < b.topk_n[:, None]], axis=1)
-            sc_key = np.where(valid, sc, -np.inf)
-            order = np.lexsort((dc, -sc_key), axis=1)[:, :k]       # per query: score desc, doc asc; invalid slots last
-            rows = np.arange(fq.n_queries)[:, None]
-            m.topk_n[:] = np.minimum(a.topk_n.astype(np.uint64) + b.topk_n, k).astype(np.uint32)
-            keep = np.arange(k)[None, :] < m.topk_n[:, None]
-            m.topk_score[:] = np.where(keep, sc[rows, order], 0.0)
-            m.topk_doc[:] = np.where(keep, dc[rows, order], 0)
-        return m
+        res = BatchResults(fq.n_queries, top_k)
+        rs = res.c_struct()
+        capi.check(self._L.pb_query_batch(self._ix, C.byref(d), C.byref(rs)))
+        return res
 
     def query_batch(self, queries: Sequence[str], score_calculator, tokenizer: Tokenizer,
                     fields_boost: Sequence[float], top_k: int = 10) -> List[List[QueryResult]]:
