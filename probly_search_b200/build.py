@@ -23,7 +23,7 @@ NVCC_COMMON = [
 ]
 LINK_FLAGS = ["-Wno-deprecated-gpu-targets", "-shared", "-cudart", "shared", "-Xlinker", "--no-as-needed", "-ldl"]
 
-HEADERS = ["kernels.cuh", "plan_kernels.cuh", "union_kernels.cuh", "field_ops.hpp", "common.hpp", "group.hpp"]
+HEADERS = ["kernels.cuh", "plan_kernels.cuh", "union_kernels.cuh", "union_warp_kernel.cuh", "field_ops.hpp", "common.hpp", "group.hpp"]
 # (object name, source, extra flags)
 UNITS = [("engine", "engine.cu", []), ("group", "group.cu", [])] + \
         [(f"kernels_f{f}", "kernels_f.cu", [f"-DPB_F={f}"]) for f in (1, 2, 3, 4)] + \

@@ -133,6 +133,7 @@ struct pb_index {
   DBuf<uint16_t> u_code[4];
   uint32_t u_wbits = 0, u_shards = 0;
   bool u_ok = false;
+  bool u_warp = false;           // union_warp_kernel (small shards, one warp per task) instead of union_kernel (2048-doc shards per CTA)
   DBuf<ull> liverowcnt_prefix, dflive_prefix;   // per-term prefixes of term_live_rows / term_df_live (class-U row statistics)
   // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
   std::vector<uint32_t> h_node_parent, h_node_char, h_term_node;
@@ -186,8 +187,13 @@ static int index_build_union(pb_index* ix) {
   }
   if (!ok) return PB_OK;                      // outside the envelope of the dense path: queries take the per-list path
   const uint64_t R = ix->n_rows, RP = R + 256;          // pad: 128-row groups are loaded whole
-  ix->u_wbits = 11;
-  if (const char* w = std::getenv("PB_UNION_WBITS")) ix->u_wbits = (uint32_t)std::min(12, std::max(7, atoi(w)));   // tuning knob
+  // two kernels: union_warp_kernel owns a 512-doc shard per WARP, union_kernel a 2048-doc shard per CTA (PB_UNION_KERNEL=cta)
+  {
+    const char* k = std::getenv("PB_UNION_KERNEL");
+    ix->u_warp = !(k && !std::strcmp(k, "cta"));
+  }
+  ix->u_wbits = ix->u_warp ? 9 : 11;
+  if (const char* w = std::getenv("PB_UNION_WBITS")) ix->u_wbits = (uint32_t)std::min(ix->u_warp ? 10 : 11, std::max(ix->u_warp ? 7 : 11, atoi(w)));   // tuning knob
   ix->u_shards = (uint32_t)(((ix->n_docs ? ix->n_docs - 1 : 0) >> ix->u_wbits) + 1);
   DBuf<uint32_t> keys, vals, keys2, vals2, row_term;
   DBuf<uint8_t> tmp;
@@ -702,8 +708,12 @@ int batch_compute(pb_batch* b) {
   up.uq = b->uq.p; up.q_isu = b->q_isu.p; up.q_isu2 = b->q_isu2.p;
   up.max_term_bytes = ix->max_term_bytes;
   for (uint32_t f = 0; f < ix->F; ++f) up.max_tf = std::max(up.max_tf, ix->max_tf[f]);
-  up.allow_gen = union_smem_bytes((int)ix->F, ix->u_wbits, true) <= (226u << 10) ? 1u : 0u;
-  if (union_smem_bytes((int)ix->F, ix->u_wbits, false) > (226u << 10)) up.enabled = 0;
+  {
+    const size_t sm_gen = ix->u_warp ? union_warp_smem_bytes((int)ix->F, ix->u_wbits, true) : union_smem_bytes((int)ix->F, ix->u_wbits, true);
+    const size_t sm_fast = ix->u_warp ? union_warp_smem_bytes((int)ix->F, ix->u_wbits, false) : union_smem_bytes((int)ix->F, ix->u_wbits, false);
+    up.allow_gen = sm_gen <= (222u << 10) ? 1u : 0u;
+    if (sm_fast > (222u << 10)) up.enabled = 0;
+  }
   up.liverowcnt_prefix = ix->liverowcnt_prefix.p; up.dflive_prefix = ix->dflive_prefix.p;
   up.stats = b->stats.p + 2 * ST_COUNT;
   plan_query_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(view, Q, b->query_term_off.p, b->qt_lo.p, b->qt_hi.p,
@@ -809,7 +819,8 @@ int batch_compute(pb_batch* b) {
   // partial top-k lists: <= 2 per warp per launch + 2 per class-G query
   const uint64_t max_warps = (uint64_t)ix->sm_count * 8 * WARPS_PER_CTA;
   const uint64_t n_gq = n_gsegs ? b->h_gidx[Q] : 0;
-  const uint64_t u_chunks = ix->u_ok ? (ix->u_shards + U_CHUNK - 1) / U_CHUNK : 0;
+  const uint64_t u_spi = ix->u_warp ? (U_ITEM_DOCS >> ix->u_wbits) : (uint64_t)U_CHUNK;      // shards per work item
+  const uint64_t u_chunks = ix->u_ok ? (ix->u_shards + u_spi - 1) / u_spi : 0;
   const uint64_t u_items = (h_nu + h_nu2) * u_chunks;
   uint64_t part_cap = 2 * max_warps * (1 + 2 * rounds.size()) + 2 * n_gq + 64 + u_items;
   if (part_cap >= 0xFFFFFFF0ull) { pb::set_error("too many partial lists"); return PB_ERR_UNSUPPORTED; }
@@ -871,13 +882,15 @@ int batch_compute(pb_batch* b) {
     UP.uq = b->uq.p; UP.u_list = list; UP.n_u = (uint32_t)nu; UP.n_chunks = (uint32_t)u_chunks;
     UP.item_counter = b->u_counter.p + gen;
     UP.prof = b->u_counter.p + 2;
-    const size_t smem = union_smem_bytes((int)ix->F, ix->u_wbits, gen != 0);
+    const size_t smem = ix->u_warp ? union_warp_smem_bytes((int)ix->F, ix->u_wbits, gen != 0) : union_smem_bytes((int)ix->F, ix->u_wbits, gen != 0);
     int per_sm = 0;
-    CU(field_ops(ix->F)->union_occupancy(gen != 0, &per_sm, smem));
+    if (ix->u_warp) CU(field_ops(ix->F)->union_warp_occupancy(gen != 0, &per_sm, smem));
+    else CU(field_ops(ix->F)->union_occupancy(gen != 0, &per_sm, smem));
     if (per_sm < 1) { pb::set_error("union kernel does not fit an SM (%zu B shared)", smem); return PB_ERR_CUDA; }
     const int grid = (int)std::min<uint64_t>((uint64_t)ix->sm_count * per_sm, nu * u_chunks);
     const int e0 = b->rev_begin();
-    CU(field_ops(ix->F)->union_launch(gen != 0, &UP, grid, smem, st));
+    if (ix->u_warp) CU(field_ops(ix->F)->union_warp_launch(gen != 0, &UP, grid, smem, st));
+    else CU(field_ops(ix->F)->union_launch(gen != 0, &UP, grid, smem, st));
     b->rev_end(3, e0);
     launches += 2;
     S.union_queries += nu;

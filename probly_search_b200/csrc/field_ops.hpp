@@ -6,6 +6,7 @@
 
 #include "kernels.cuh"
 #include "union_kernels.cuh"
+#include "union_warp_kernel.cuh"
 
 namespace pbk {
 
@@ -20,6 +21,8 @@ struct FieldOps {
                                 cudaStream_t st);
   cudaError_t (*union_occupancy)(bool gen, int* per_sm, size_t smem);
   cudaError_t (*union_launch)(bool gen, const UnionParams* P, int grid, size_t smem, cudaStream_t st);
+  cudaError_t (*union_warp_occupancy)(bool gen, int* per_sm, size_t smem);
+  cudaError_t (*union_warp_launch)(bool gen, const UnionParams* P, int grid, size_t smem, cudaStream_t st);
 };
 
 const FieldOps* field_ops_f1();

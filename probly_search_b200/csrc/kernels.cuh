@@ -346,6 +346,23 @@ struct WarpAcc {
     if (o.k) insert_candidates(valid && better(s, doc, thr_s, thr_d), doc, s, lane, (int)o.k);
   }
 
+  // add() for scores that are >= +0.0 (ZeroToOne): the top-k pre-test compares bit patterns as signed integers
+  // (doubles of one sign order like their bits; the threshold is -1.0 or such a score) instead of f64 compares.
+  __device__ __forceinline__ void add_nonneg(const Outputs& o, bool valid, uint32_t doc, double s, int lane) {
+    if (valid) {
+      ++cnt;
+      uint32_t a = doc_mix(doc);
+      dd += sq64(a);
+      sd += sq64(score_mix(a, s));
+    }
+    if (o.full_q) capture(o, valid, doc, s, lane);
+    if (o.k) {
+      const long long sb = __double_as_longlong(s), tb = __double_as_longlong(thr_s);
+      const bool cand = valid && (sb > tb || (sb == tb && doc < thr_d));
+      if (__any_sync(0xffffffffu, cand)) insert_candidates(cand, doc, s, lane, (int)o.k);
+    }
+  }
+
   // Four rows per lane at once (the scoring kernel's tile shape).  `some` = 4-bit mask of rows
   // that produced a result.  The top-k structure is only touched when some lane holds a score
   // that reaches the current k-th best.

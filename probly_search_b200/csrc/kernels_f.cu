@@ -98,8 +98,23 @@ cudaError_t union_launch(bool gen, const UnionParams* P, int grid, size_t smem, 
   return cudaGetLastError();
 }
 
+template <bool GEN>
+cudaError_t union_warp_occ_t(int* per_sm, size_t smem) {
+  cudaError_t e = raise_smem_limit(union_warp_kernel<F, GEN>, smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, union_warp_kernel<F, GEN>, U_W_THREADS, smem);
+}
+cudaError_t union_warp_occupancy(bool gen, int* per_sm, size_t smem) {
+  return gen ? union_warp_occ_t<true>(per_sm, smem) : union_warp_occ_t<false>(per_sm, smem);
+}
+cudaError_t union_warp_launch(bool gen, const UnionParams* P, int grid, size_t smem, cudaStream_t st) {
+  if (gen) union_warp_kernel<F, true><<<grid, U_W_THREADS, smem, st>>>(*P);
+  else union_warp_kernel<F, false><<<grid, U_W_THREADS, smem, st>>>(*P);
+  return cudaGetLastError();
+}
+
 const FieldOps OPS = {score_occupancy, score_launch, mark_launch, fold_launch, binfold_launch, live_df_launch,
-                      union_occupancy, union_launch};
+                      union_occupancy, union_launch, union_warp_occupancy, union_warp_launch};
 
 }  // namespace
 

@@ -19,11 +19,14 @@ pytestmark = pytest.mark.gpu
 def _route(monkeypatch, route):
     if route == "union_all":
         monkeypatch.setenv("PB_UNION_MIN_DIV", "0")
+    elif route == "union_cta":                       # the CTA-per-2048-doc-shard kernel instead of the warp-per-512-doc-shard one
+        monkeypatch.setenv("PB_UNION_MIN_DIV", "0")
+        monkeypatch.setenv("PB_UNION_KERNEL", "cta")
     elif route == "union_off":
         monkeypatch.setenv("PB_UNION", "0")
 
 
-@pytest.mark.parametrize("route", ["union_all", "union_off"])
+@pytest.mark.parametrize("route", ["union_all", "union_cta", "union_off"])
 @pytest.mark.parametrize("seed", range(6))
 def test_random_corpora_through_both_routes(monkeypatch, route, seed):
     _route(monkeypatch, route)
@@ -40,7 +43,8 @@ def test_random_corpora_through_both_routes(monkeypatch, route, seed):
     compare_queries(ix, o, queries[:30] + queries[-10:], [1.0] * n_fields, f"{route} seed={seed} removed")
 
 
-def test_term_pools_and_consumed_query_terms(monkeypatch):
+@pytest.mark.parametrize("route", ["union_all", "union_cta"])
+def test_term_pools_and_consumed_query_terms(monkeypatch, route):
     """zero_to_one.rs:98-121 on nested prefixes: the same expanded term reached from two query terms shares one
     pool of tf uses, a refused entry does not consume its query term, ties keep (query term, expansion) order."""
     _route(monkeypatch, "union_all")
@@ -76,7 +80,7 @@ def test_queries_outside_the_dense_envelope_take_the_list_route(monkeypatch):
     assert b.stats()["union_queries"] == 2
 
 
-@pytest.mark.parametrize("route,removed", [("default", False), ("union_all", False), ("union_all", True), ("union_off", False)])
+@pytest.mark.parametrize("route,removed", [("default", False), ("union_all", False), ("union_all", True), ("union_cta", True), ("union_off", False)])
 def test_scaled_cfg2_counts_digests_topk(monkeypatch, route, removed):
     _route(monkeypatch, route)
     cfg = W.CONFIGS["cfg2"]
