@@ -847,6 +847,10 @@ int batch_compute(pb_batch* b) {
   for (int f = 0; f < 4; ++f) { P.boost[f] = b->boost[f]; P.avg[f] = ix->avg[f]; P.tab_tfcap[f] = b->tab_tfcap[f]; P.tab_flcap[f] = b->tab_flcap[f]; P.tab_off[f] = b->tab_off[f]; }
   P.tab = b->tab.p; P.tab_total = b->scorer == 0 ? b->tab_total : 0;
   P.tab_full = b->tab_full ? 1u : 0u;
+  // tiles PB_L2_AHEAD ahead are pulled into L2 (measured on cfg 1, whose image is only 207 MB: 25.1 ms with the prefetch,
+  // 28.6 ms without — it pays even when 90 % of the sectors hit L2); PB_L2_PREFETCH=0 switches it off for experiments
+  P.l2_prefetch = 1u;
+  if (const char* e = std::getenv("PB_L2_PREFETCH")) P.l2_prefetch = atoi(e) ? 1u : 0u;
   P.boosts_all_one = 1u;
   for (uint32_t f = 0; f < ix->F; ++f) if (b->boost[f] != 1.0) P.boosts_all_one = 0u;
   P.doc_bits = doc_bits; P.bitmap_words = bitmap_words; P.bitmap_sum_words = bitmap_sum_words; P.bitmap_doc_words = bitmap_doc_words;

@@ -171,6 +171,7 @@ struct ScoreParams {
   // (tf, fl) values are.  tab_stride = 8 << tab_rep_shift bytes, tab_boff[f] = tab_off[f] * tab_stride.
   uint32_t tab_rep_shift, tab_stride, tab_boff[4];
   uint32_t boosts_all_one;       // every fields_boost is exactly 1.0
+  uint32_t l2_prefetch;          // the posting image is far larger than L2 (streams from HBM): prefetch tiles ahead into L2
   // side path
   uint32_t* bitmap;              // pool of the round: query q's words start at q_bmoff[q] - round_bm0
   const unsigned long long* q_bmoff;   // [n_queries + 1] exclusive prefix of the per-query word counts
@@ -929,6 +930,9 @@ __device__ __forceinline__ void process_tile(const ScoreParams& P, const uint32_
 // flight while tile i is scored (the spare tile behind the last row and the pad words of the row
 // masks make the look-ahead load safe; nothing read ahead is used or cleared unless it is scored).
 // The tile and mask addresses advance by constants: no 64-bit index arithmetic in the loop.
+// (Round 3 tried a compile-time PRIMARY specialisation of this loop — no mask code at all for non-primary segments,
+// no run-time flag for primary ones: class-G launch 18.4 ms instead of 15.6 in an alternating A/B on one box.  The
+// shared loop below stays.)
 template <int F, int SCORER, bool GMODE, bool FAST, int SIMPLE, bool NARROW>
 __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                                uint64_t tile_row, uint32_t n_tiles, int lane, WarpAcc& acc,
@@ -957,7 +961,7 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
 #if PB_L2_AHEAD
       // an image larger than L2 (cfg 3/4: 2.1 GB) streams from HBM: one tile of register look-ahead does
       // not cover DRAM latency, so the lines of the tile PB_L2_AHEAD tiles further on are pulled into L2
-      if (i + PB_L2_AHEAD < n_tiles && lane < (int)(TileGeom<F, NARROW>::WORDS / 32))
+      if (P.l2_prefetch && i + PB_L2_AHEAD < n_tiles && lane < (int)(TileGeom<F, NARROW>::WORDS / 32))
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + PB_L2_AHEAD * TileGeom<F, NARROW>::WORDS + lane * 32));
 #endif
       const uint32_t mw2 = ld_mask(maskp + 8);       // mask of tile i + 2
