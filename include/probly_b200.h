@@ -170,6 +170,16 @@ void pb_image_file_free(pb_image_file* f);
  * ---------------------------------------------------------------------------------------- */
 int pb_device_count(void);
 int pb_index_create(const pb_index_image* image, int device, pb_index** out);
+/* GPU index construction: the posting columns are flattened ON THE DEVICE.  The host builder keeps
+ * what it always kept — the trie, the term dictionary and an append log of (term, doc, tf) tuples in document
+ * order (tokenising and hashing, src/index.rs:77-158) — and flattens only the small structures; the device sorts the
+ * tuples by term ordinal (cub radix sort, stable: docs stay ascending), derives max tf / field length, picks the
+ * layout and writes the tile-blocked columns where the scoring kernels read them.  from_doc_ordinal > 0 builds a
+ * delta segment (pb_builder_flatten_from).  pb_builder_flatten_structure returns that image WITHOUT posting columns
+ * (post_blocks = NULL, max_tf = max_fl = 0): node / term arrays, doc keys and the live state, which is all a caller
+ * needs next to the pb_index. */
+int pb_index_create_from_builder(pb_builder* b, uint64_t from_doc_ordinal, int device, pb_index** out);
+int pb_builder_flatten_structure(pb_builder* b, uint64_t from_doc_ordinal, pb_index_image* out);
 /* New removed set / N / avg after remove_document WITHOUT re-flattening (pre-vacuum state,
  * SURVEY §3.4 rule 9).  removed_ords is the FULL set of removed ordinals.  Recomputes the
  * per-term live occurrence count (count_documents, index.rs:282-297) on the device and the

@@ -101,7 +101,7 @@ EXPORTS = [
     "pb_batch_fetch_gathered", "pb_batch_device_gathered",
     "pb_group_create", "pb_group_size", "pb_group_set_live_state", "pb_group_query_batch", "pb_group_member_stats",
     "pb_group_destroy",
-    "pb_builder_flatten_from", "pb_builder_flatten_term_ids", "pb_index_set_df_extra", "pb_index_attach_delta",
+    "pb_builder_flatten_from", "pb_builder_flatten_term_ids", "pb_index_set_df_extra", "pb_index_attach_delta", "pb_index_create_from_builder", "pb_builder_flatten_structure",
 ]
 PB_COMM_ID_BYTES = 128
 
@@ -182,6 +182,8 @@ def lib() -> C.CDLL:
         "pb_builder_flatten_term_ids": (i32, [vp, vp, u64, P(u64)]),
         "pb_index_set_df_extra": (i32, [vp, vp, u64]),
         "pb_index_attach_delta": (i32, [vp, vp, vp, u64, vp, u64]),
+        "pb_index_create_from_builder": (i32, [vp, u64, i32, P(vp)]),
+        "pb_builder_flatten_structure": (i32, [vp, u64, P(IndexImage)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -200,6 +200,7 @@ struct Builder {
 
   // flatten outputs (owned here, handed out as raw pointers)
   bool flat_valid = false;
+  bool flat_posts = false;               // the flattened image carries the host posting columns (post_blocks)
   uint64_t flat_from = 0;                // first doc ordinal whose rows the flattened image holds (0 = all: the full image)
   std::vector<uint32_t> f_term_id;       // DFS term ordinal of the last flatten -> builder term id (stable across flattens)
   std::vector<uint32_t> f_node_edge_begin, f_node_term_lo, f_node_term_hi, f_node_parent, f_node_char;
@@ -391,20 +392,26 @@ struct Builder {
 
   // from_doc = 0: the whole index.  from_doc > 0: a DELTA segment — the current trie (so that its expansion order is
   // the global one) with the posting rows of the docs whose ordinal is >= from_doc only.
-  int flatten(pb_index_image* out, uint64_t from_doc = 0) {
+  // with_posts = false: everything but the posting columns (post_blocks = NULL, max_tf / max_fl = 0) — the device
+  // builds the columns itself from the append log (pb_index_create_from_builder).
+  int flatten(pb_index_image* out, uint64_t from_doc = 0, bool with_posts = true) {
     if (from_doc > doc_key.size()) { set_error("flatten: first doc ordinal %llu beyond the index", (unsigned long long)from_doc); return PB_ERR_INVALID; }
-    if (!flat_valid || flat_from != from_doc) {
+    if (!flat_valid || flat_from != from_doc || (with_posts && !flat_posts)) {
       flat_valid = false;
-      int rc = do_flatten(from_doc);
+      int rc = do_flatten(from_doc, with_posts);
       if (rc != PB_OK) return rc;
       flat_valid = true;
+      flat_posts = with_posts;
       flat_from = from_doc;
     }
     *out = image;
+    if (!with_posts) { out->post_blocks = nullptr; for (uint32_t f = 0; f < PB_MAX_FIELDS; ++f) { out->max_tf[f] = 0; out->max_fl[f] = 0; } }
     return PB_OK;
   }
 
-  int do_flatten(uint64_t from_doc) {
+  std::vector<uint32_t> f_ord_of;        // builder term id -> DFS term ordinal of the last flatten (NONE: not in it)
+
+  int do_flatten(uint64_t from_doc, bool with_posts) {
     const size_t NN = nodes.size();
     // rows per term inside the flattened doc range
     const uint64_t log_from = doc_log_begin[from_doc];
@@ -480,7 +487,8 @@ struct Builder {
       }
     }
     // posting columns: counting sort of the log by DFS term ordinal (stable -> docs ascend)
-    std::vector<uint32_t> ord_of(dict.size(), NONE);
+    std::vector<uint32_t>& ord_of = f_ord_of;
+    ord_of.assign(dict.size(), NONE);
     for (size_t t = 0; t < NT; ++t) ord_of[term_old[t]] = (uint32_t)t;
     f_term_row_begin.assign(NT + 1, 0);
     for (size_t t = 0; t < NT; ++t) f_term_row_begin[t + 1] = f_term_row_begin[t] + rows_of[term_old[t]];
@@ -489,9 +497,11 @@ struct Builder {
     f_term_id = term_old;
     const uint64_t NRP = ((NR + 127) / 128 + 1) * 128;     // pad: whole 128-row tiles + one spare tile
     const uint32_t NCOL = 1 + 2 * F;
-    f_post_blocks.assign(NRP * NCOL, 0);
     uint32_t max_tf[PB_MAX_FIELDS] = {0, 0, 0, 0}, max_fl[PB_MAX_FIELDS] = {0, 0, 0, 0};
-    {
+    if (!with_posts) {
+      std::vector<uint32_t>().swap(f_post_blocks);      // the device builds the columns from the log
+    } else {
+      f_post_blocks.assign(NRP * NCOL, 0);
       std::vector<uint64_t> fill(f_term_row_begin.begin(), f_term_row_begin.end() - 1);
       for (uint64_t li = log_from; li < log.size(); ++li) {
         const Tuple& tp = log[li];
@@ -542,6 +552,22 @@ struct Builder {
 }  // namespace pb
 
 struct pb_builder { pb::Builder impl; explicit pb_builder(uint32_t f) : impl(f) {} };
+
+namespace pb {
+static_assert(sizeof(Tuple) == sizeof(LogTuple) && alignof(Tuple) == alignof(LogTuple), "the log tuple is shared with the engine");
+int builder_flatten_structure(pb_builder* b, uint64_t from_doc, pb_index_image* im, BuilderLogView* view) {
+  Builder& B = b->impl;
+  int rc = B.flatten(im, from_doc, false);
+  if (rc != PB_OK) return rc;
+  const uint64_t log_from = B.doc_log_begin[from_doc];
+  view->F = B.F;
+  view->tuples = reinterpret_cast<const LogTuple*>(B.log.data()) + log_from;
+  view->n_tuples = B.log.size() - log_from;
+  view->doc_fl = B.doc_fl.data(); view->n_docs = B.doc_key.size();
+  view->ord_of = B.f_ord_of.data(); view->n_ord = B.f_ord_of.size();
+  return PB_OK;
+}
+}  // namespace pb
 
 extern "C" {
 

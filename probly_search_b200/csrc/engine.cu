@@ -1211,8 +1211,34 @@ int pb_device_count(void) {
   return n;
 }
 
+static int index_create_impl(const pb_index_image* im, const pb::BuilderLogView* log, int device, pb_index** out);
+
 int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
   if (!im || !out) { pb::set_error("pb_index_create: null argument"); return PB_ERR_INVALID; }
+  if (!im->post_blocks) { pb::set_error("pb_index_create: the image has no posting columns (a structure-only flatten goes through pb_index_create_from_builder)"); return PB_ERR_INVALID; }
+  return index_create_impl(im, nullptr, device, out);
+}
+
+int pb_index_create_from_builder(pb_builder* b, uint64_t from_doc_ordinal, int device, pb_index** out) {
+  if (!b || !out) { pb::set_error("pb_index_create_from_builder: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    pb_index_image im;
+    pb::BuilderLogView log;
+    RC(pb::builder_flatten_structure(b, from_doc_ordinal, &im, &log));
+    return index_create_impl(&im, &log, device, out);
+  });
+}
+
+int pb_builder_flatten_structure(pb_builder* b, uint64_t from_doc_ordinal, pb_index_image* out) {
+  if (!b || !out) { pb::set_error("pb_builder_flatten_structure: null argument"); return PB_ERR_INVALID; }
+  PB_TRY({
+    pb::BuilderLogView log;
+    return pb::builder_flatten_structure(b, from_doc_ordinal, out, &log);
+  });
+}
+
+// `log` != NULL: the posting columns are flattened ON THE DEVICE from the builder's append log (the image carries none)
+static int index_create_impl(const pb_index_image* im, const pb::BuilderLogView* log, int device, pb_index** out) {
   if (im->version != 1 || im->num_fields == 0 || im->num_fields > PB_MAX_FIELDS) { pb::set_error("pb_index_create: bad image header"); return PB_ERR_INVALID; }
   if (im->n_rows_padded % TILE_ROWS != 0 || im->n_rows_padded < im->n_rows + TILE_ROWS) { pb::set_error("pb_index_create: posting columns must be padded to whole 128-row tiles plus one spare tile"); return PB_ERR_INVALID; }
   int ndev = 0;
@@ -1225,8 +1251,9 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
   if (device < 0 || device >= ndev) { pb::set_error("pb_index_create: device %d out of range (0..%d)", device, ndev - 1); return PB_ERR_INVALID; }
   PB_TRY({
     // the kernels index with the image's offsets / ordinals unchecked and the u16 posting codes are sized from
-    // max_tf / max_fl: refuse an inconsistent image here (PB_TRUST_IMAGE=1 skips the O(rows) pass)
-    if (!(std::getenv("PB_TRUST_IMAGE") && !std::strcmp(std::getenv("PB_TRUST_IMAGE"), "1"))) RC(pb::validate_image(im));
+    // max_tf / max_fl: refuse an inconsistent image here (PB_TRUST_IMAGE=1 skips the O(rows) pass).  The builder's own
+    // output (log != NULL) is trusted.
+    if (!log && !(std::getenv("PB_TRUST_IMAGE") && !std::strcmp(std::getenv("PB_TRUST_IMAGE"), "1"))) RC(pb::validate_image(im));
     CU(cudaSetDevice(device));
     pb_index* ix = new pb_index();
     std::unique_ptr<pb_index> guard(ix);
@@ -1247,10 +1274,31 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
     // u16 code = tf << fl_bits | fl per field (4 + 2F bytes per row instead of 4 + 8F); the code is
     // also the index into the field's BM25 table.  PB_POSTING_LAYOUT=wide|narrow|auto (default auto).
     {
+      // device-side flatten, part 1: sort keys + the exact maxima that decide the layout
+      DBuf<uint8_t> d_log;
+      DBuf<uint32_t> d_doc_fl, d_ord, d_keys, d_vals, d_keys2, d_vals2, d_max;
+      if (log) {
+        const uint64_t n = log->n_tuples;
+        if (n != im->n_rows) { pb::set_error("pb_index_create_from_builder: the log holds %llu tuples, the image %llu rows", (ull)n, (ull)im->n_rows); return PB_ERR_INVALID; }
+        CU(d_log.ensure(std::max<uint64_t>(n, 1) * sizeof(pb::LogTuple)));
+        if (n) CU(cudaMemcpy(d_log.p, log->tuples, n * sizeof(pb::LogTuple), cudaMemcpyHostToDevice));
+        CU(upload(d_doc_fl, log->doc_fl, log->n_docs * log->F));
+        CU(upload(d_ord, log->ord_of, log->n_ord));
+        CU(d_keys.ensure(n + 1)); CU(d_vals.ensure(n + 1)); CU(d_keys2.ensure(n + 1)); CU(d_vals2.ensure(n + 1));
+        CU(d_max.ensure(8));
+        if (n) {
+          flat_keys_kernel<<<ix->sm_count * 8, 256>>>(reinterpret_cast<const FlatTuple*>(d_log.p), n, d_ord.p, d_doc_fl.p, ix->F,
+                                                     d_keys.p, d_vals.p, d_max.p);
+          CU(cudaGetLastError());
+        }
+        uint32_t h_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CU(cudaMemcpy(h_max, d_max.p, sizeof(h_max), cudaMemcpyDeviceToHost));
+        for (uint32_t f = 0; f < ix->F; ++f) { ix->max_tf[f] = h_max[f]; ix->max_fl[f] = h_max[4 + f]; }
+      }
       bool fits = true;
       for (uint32_t f = 0; f < ix->F; ++f) {
-        ix->fl_bits[f] = bits_for((uint64_t)im->max_fl[f] + 1);
-        fits = fits && (((uint64_t)im->max_tf[f] + 1) << ix->fl_bits[f]) <= 65536ull;
+        ix->fl_bits[f] = bits_for((uint64_t)ix->max_fl[f] + 1);
+        fits = fits && (((uint64_t)ix->max_tf[f] + 1) << ix->fl_bits[f]) <= 65536ull;
       }
       uint64_t min_table = 0;       // the BM25 table keeps whole rows of 1 << fl_bits entries in the narrow layout
       for (uint32_t f = 0; f < ix->F; ++f) min_table += 4ull << ix->fl_bits[f];
@@ -1260,7 +1308,27 @@ int pb_index_create(const pb_index_image* im, int device, pb_index** out) {
       ix->narrow = fits && !(e && !std::strcmp(e, "wide"));
       const uint32_t NC = 1 + 2 * ix->F;
       const uint64_t tiles = im->n_rows_padded / TILE_ROWS;
-      if (!ix->narrow) {
+      if (log) {
+        // part 2: stable radix sort by term ordinal (the log is in document order, so docs ascend inside a term), then
+        // the tiles are written where they will be read
+        ix->tile_words = ix->narrow ? TILE_ROWS + ix->F * (TILE_ROWS / 2) : NC * TILE_ROWS;
+        CU(ix->post_blocks.ensure((size_t)(tiles + 1) * ix->tile_words + 1));      // zero-filled: pad rows, spare tile
+        const uint64_t n = log->n_tuples;
+        if (n) {
+          const int end_bit = (int)bits_for(std::max<uint64_t>(im->n_terms, 2));
+          size_t bytes = 0;
+          DBuf<uint8_t> tmp;
+          CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p, (int64_t)n, 0, end_bit));
+          CU(tmp.ensure(bytes));
+          bytes = tmp.cap;
+          CU(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p, (int64_t)n, 0, end_bit));
+          flat_gather_kernel<<<(unsigned)((n + 255) / 256), 256>>>(reinterpret_cast<const FlatTuple*>(d_log.p), d_vals2.p, n, d_doc_fl.p,
+                                                                   ix->F, ix->narrow ? 1u : 0u, ix->tile_words, ix->fl_bits[0],
+                                                                   ix->fl_bits[1], ix->fl_bits[2], ix->fl_bits[3], ix->post_blocks.p);
+          CU(cudaGetLastError());
+          CU(cudaDeviceSynchronize());
+        }
+      } else if (!ix->narrow) {
         ix->tile_words = NC * TILE_ROWS;
         CU(upload(ix->post_blocks, im->post_blocks, im->n_rows_padded * NC, (size_t)TILE_ROWS * NC));
       } else {

@@ -273,6 +273,53 @@ __global__ void ubuild_bounds_kernel(const uint32_t* __restrict__ sorted_keys, u
   shard_row[s] = (uint32_t)lo;
 }
 
+// ---- device-side flatten of the posting columns (pb_index_create_from_builder) -----------------
+// The host builder keeps an append log of (term id, doc, tf[F]) tuples in document order.  Pass 1: sort key = the
+// term's DFS ordinal (+ the exact maxima of tf / field length that decide the column layout).  A stable radix sort
+// of (key, tuple index) then puts the rows of a term together with their docs ascending; pass 2 writes the tile-blocked
+// columns (u16 codes or u32 columns) straight into HBM: the host never materialises them.
+struct FlatTuple { uint32_t term, doc, tf[4]; };
+__global__ void flat_keys_kernel(const FlatTuple* __restrict__ t, uint64_t n, const uint32_t* __restrict__ ord_of,
+                                 const uint32_t* __restrict__ doc_fl, uint32_t F, uint32_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals, uint32_t* __restrict__ maxima) {
+  uint32_t mtf[4] = {0, 0, 0, 0}, mfl[4] = {0, 0, 0, 0};
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const FlatTuple tp = t[i];
+    keys[i] = ord_of[tp.term];
+    vals[i] = (uint32_t)i;
+    for (uint32_t f = 0; f < F; ++f) { mtf[f] = max(mtf[f], tp.tf[f]); mfl[f] = max(mfl[f], doc_fl[(uint64_t)tp.doc * F + f]); }
+  }
+  for (uint32_t f = 0; f < F; ++f) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mtf[f] = max(mtf[f], __shfl_xor_sync(0xffffffffu, mtf[f], o));
+      mfl[f] = max(mfl[f], __shfl_xor_sync(0xffffffffu, mfl[f], o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&maxima[f], mtf[f]); atomicMax(&maxima[4 + f], mfl[f]); }
+  }
+}
+__global__ void flat_gather_kernel(const FlatTuple* __restrict__ t, const uint32_t* __restrict__ sorted_idx, uint64_t n,
+                                   const uint32_t* __restrict__ doc_fl, uint32_t F, uint32_t narrow, uint32_t tile_words,
+                                   uint32_t fb0, uint32_t fb1, uint32_t fb2, uint32_t fb3, uint32_t* __restrict__ post) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const FlatTuple tp = t[sorted_idx[r]];
+  const uint32_t fl_bits[4] = {fb0, fb1, fb2, fb3};
+  uint32_t* tile = post + (r / TILE_ROWS) * (uint64_t)tile_words;
+  const uint32_t in = (uint32_t)(r % TILE_ROWS);
+  tile[in] = tp.doc;
+  if (narrow) {
+    uint16_t* codes = reinterpret_cast<uint16_t*>(tile + TILE_ROWS);
+    for (uint32_t f = 0; f < F; ++f)
+      codes[f * TILE_ROWS + in] = (uint16_t)((tp.tf[f] << fl_bits[f]) | doc_fl[(uint64_t)tp.doc * F + f]);
+  } else {
+    for (uint32_t f = 0; f < F; ++f) {
+      tile[(1 + f) * TILE_ROWS + in] = tp.tf[f];
+      tile[(1 + F + f) * TILE_ROWS + in] = doc_fl[(uint64_t)tp.doc * F + f];
+    }
+  }
+}
+
 // One warp per query term of a class-G query: writes one SECONDARY segment per live expanded
 // term, in expansion order, and elects the query's largest list (atomicMax on rows<<32|seg).
 __global__ void gfill_kernel(IndexView ix, uint64_t n_qterms, const uint64_t* __restrict__ query_term_off,

@@ -247,6 +247,12 @@ class Index:
     DELTA_MAX_FRACTION = 0.25
     DELTA_MIN_ROWS = 1 << 16
 
+    def _structure(self, from_doc: int) -> capi.IndexImage:
+        """The image without posting columns (pb_builder_flatten_structure): node / term arrays, doc keys, live state."""
+        im = capi.IndexImage()
+        capi.check(self._L.pb_builder_flatten_structure(self._require_builder(), int(from_doc), C.byref(im)))
+        return im
+
     def _term_ids_of_last_flatten(self) -> np.ndarray:
         n = C.c_uint64(0)
         self._L.pb_builder_flatten_term_ids(self._b, None, 0, C.byref(n))
@@ -306,20 +312,21 @@ class Index:
                 self._image_dirty = True                  # the delta has grown: fold it into the main image
         if self._ix is None or self._image_dirty:
             self._drop_delta()
-            im = self.flatten()
             if self._ix is not None:
                 self._drop_device_index()
+            # the posting columns are flattened on the device from the builder's append log; the host flattens the
+            # small structures only (trie, term table, doc keys, live state)
             h = C.c_void_p()
-            capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
+            capi.check(self._L.pb_index_create_from_builder(self._require_builder(), 0, self.device, C.byref(h)))
+            im = self._structure(0)
             self._ix = h
             self._n_main_docs, self._n_main_rows = int(im.n_docs), int(im.n_rows)
             self._sid_main = self._term_ids_of_last_flatten()
             self._apply_live_state(im)
         elif self._delta_dirty:
-            im = capi.IndexImage()
-            capi.check(self._L.pb_builder_flatten_from(self._require_builder(), self._n_main_docs, C.byref(im)))
             h = C.c_void_p()
-            capi.check(self._L.pb_index_create(C.byref(im), self.device, C.byref(h)))
+            capi.check(self._L.pb_index_create_from_builder(self._require_builder(), self._n_main_docs, self.device, C.byref(h)))
+            im = self._structure(self._n_main_docs)
             self._sid_delta = self._term_ids_of_last_flatten()
             # pb_index_attach_delta: the main image takes ownership (a previous delta is destroyed), the two segments
             # exchange their per-term live counts, and the query entry points answer for both from now on
@@ -331,11 +338,7 @@ class Index:
             self._ix_delta = h
             self._apply_live_state(im)
         else:                                             # only remove_document happened
-            if self._ix_delta is not None:
-                im = capi.IndexImage()
-                capi.check(self._L.pb_builder_flatten_from(self._require_builder(), self._n_main_docs, C.byref(im)))
-            else:
-                im = self.flatten()
+            im = self._structure(self._n_main_docs if self._ix_delta is not None else 0)
             self._apply_live_state(im)
         self._image_dirty = self._live_dirty = self._delta_dirty = False
 

@@ -108,3 +108,43 @@ def test_staged_batches_and_images_see_one_segment():
     for q, text in enumerate(QUERIES):
         assert int(got.n_results[q]) == len(o.query(text, orc.BM25, [1.0, 1.0]))
     assert ix.expand_term("ab") == o.expand_term("ab")
+
+
+@pytest.mark.parametrize("layout", ["auto", "wide"])
+def test_device_side_flatten_equals_the_host_flattened_image(monkeypatch, layout):
+    """pb_index_create_from_builder sorts the builder's (term, doc, tf) log on the device and writes the
+    tile-blocked posting columns itself.  The image it builds must answer exactly like the one uploaded from the
+    host-flattened pb_index_image (same layout decision, same rows in the same order)."""
+    import ctypes as C
+    from probly_search_b200 import workload as W
+    monkeypatch.setenv("PB_POSTING_LAYOUT", layout)
+    cfg = W.CONFIGS["cfg2"]
+    wl = W.Workload(cfg, n_docs=30_000, vocab=1 << 12)
+    ix = Index(cfg.n_fields)
+    wl.build_into(ix)
+    for d in range(0, 30_000, 17):
+        ix.remove_document(d)
+    L = capi.lib()
+    ix.sync_device()                                   # device-side flatten (the default path of the host mirror)
+    im = ix.flatten()                                  # the host-flattened image with its posting columns
+    h = C.c_void_p()
+    capi.check(L.pb_index_create(C.byref(im), 0, C.byref(h)))
+    la, lb = capi.DeviceLayout(), capi.DeviceLayout()
+    capi.check(L.pb_index_device_layout(ix._ix, C.byref(la)))
+    capi.check(L.pb_index_device_layout(h, C.byref(lb)))
+    assert (la.narrow, la.bytes_per_row, la.posting_bytes, list(la.fl_bits)) == (lb.narrow, lb.bytes_per_row, lb.posting_bytes, list(lb.fl_bits))
+    assert bool(la.narrow) == (layout == "auto")
+    from probly_search_b200.index import BatchResults
+    for scorer, mode in ((score.bm25.new(), 0), (score.zero_to_one.new(), 1)):
+        fq = wl.queries(300, mode=mode)
+        d, _keep = ix._desc(fq, scorer, cfg.boosts, 10)
+        outs = []
+        for handle in (ix._ix, h):
+            r = BatchResults(fq.n_queries, 10)
+            rs = r.c_struct()
+            capi.check(L.pb_query_batch(handle, C.byref(d), C.byref(rs)))
+            outs.append(r)
+        for name in ("n_results", "doc_digest", "score_digest", "topk_n", "topk_doc", "topk_score"):
+            np.testing.assert_array_equal(getattr(outs[0], name), getattr(outs[1], name), err_msg=name)
+        assert int(outs[0].n_results.sum()) > 0
+    L.pb_index_destroy(h)
