@@ -499,7 +499,7 @@ def run_config(ctx, cfg):
                    "rows": st["rows_streamed_direct"], "bytes_per_row": bpr, "launches": st["score_launches"]},
         "side_score": {"kernel": f"pbk::score_kernel<F={F},{cfg.scorer},divert,{layout_name}>", "ms": acc["ms_side_score"],
                        "rows": st["rows_streamed_side"], "bytes_per_row": bpr, "launches": st["side_rounds"]},
-        "union": {"kernel": f"pbk::union_kernel<F={F}>", "ms": acc["ms_union"], "rows": st["rows_streamed_union"],
+        "union": {"kernel": f"pbk::union_warp_kernel<F={F}> (PB_UNION_KERNEL=cta: pbk::union_kernel)", "ms": acc["ms_union"], "rows": st["rows_streamed_union"],
                   "bytes_per_row": 8 + 2 * F, "launches": 1 if st["union_queries"] else 0},
         "side_mark": {"kernel": f"pbk::mark_kernel<F={F}>", "ms": acc["ms_side_mark"], "rows": None, "bytes_per_row": None,
                       "launches": st["side_rounds"]},
@@ -535,6 +535,8 @@ def run_config(ctx, cfg):
                                       "frac": achieved * bpr_survey / dom["bytes_per_row"] / peak if dom_name != "union" else None,
                                       "note": "SURVEY §8(d) counts the u32 columns (4 + 8F B/row); the device reads fewer bytes for the same rows"},
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                "ncu": {k2: tr[k2] for k2 in ("issue_active_pct", "lts_sector_hit_rate_pct", "warp_instructions", "duration_ms_under_ncu",
+                                             "captured_at_commit") if tr and k2 in tr} or None,
                 "hbm_resident": not image_fits_l2,
                 "note": ("the posting image is within ~2x of the 126 MB L2 and the queries are Zipf-drawn: most sectors hit L2, so "
                          "`frac` is layout bytes over the HBM peak, NOT a DRAM utilisation; compare with l2_ceiling_frac and the "
