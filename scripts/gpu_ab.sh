@@ -6,8 +6,8 @@ for v in "$@"; do
   python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/ab_$v.json"))
-    print("$v", round(d["ms_per_step"],2), {k:round(x,2) for k,x in d["stage_ms"].items()}, "e2e", round(d["e2e"]["ms_per_step"],2))
+    d=json.loads([l for l in open("gpurun_out/ab_$v.json") if l.startswith('{')][-1])
+    print("$v", round(d["ms_per_step"],2), {k:round(x,2) for k,x in d["stage_ms"].items()}, "e2e", round(d["e2e"]["ms_per_step"],2), {k:round(v["ms"],2) for k,v in d["roofline"]["classes"].items() if v["ms"]>0.01}, "parity", d["parity"].get("golden_ok"))
 except Exception as e:
     print("$v failed", e)
 PY
