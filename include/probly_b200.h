@@ -75,6 +75,9 @@ typedef struct pb_doc_tokens {
 
 int pb_builder_create(uint32_t num_fields, pb_builder** out);          /* Index::new, index.rs:37 */
 void pb_builder_destroy(pb_builder* b);
+/* Deviation from the reference, stated on purpose: adding a key that is live, or removed but not yet vacuumed,
+ * returns PB_ERR_INVALID (the reference accepts it and leaves two posting chains for one key - undefined results,
+ * SURVEY rule 13).  After pb_builder_vacuum the key may be added again. */
 int pb_builder_add_document(pb_builder* b, uint64_t key, const pb_doc_tokens* doc); /* index.rs:77 */
 /* Bulk add: n_docs documents, every field has exactly one value; field_tok_count is
  * [n_docs * num_fields]; tokens concatenated in (doc, field, token) order. */
