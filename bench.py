@@ -285,14 +285,14 @@ def get_index(ctx, cfg, n_docs, vocab):
     from probly_search_b200 import workload as W
     torch, dist = ctx["torch"], ctx["dist"]
     rank, world, dev = ctx["rank"], ctx["world"], ctx["local_rank"]
-    key = (cfg.cfg, n_docs, vocab)
+    key = (cfg.cfg, n_docs, vocab, cfg.n_fields, bool(getattr(cfg, 'bench_shape', False)))   # cfg3 / cfg4 share one corpus
     wl = W.Workload(cfg, n_docs=n_docs, vocab=vocab)
     if key in ctx["index_cache"]:
         _, ix, state = ctx["index_cache"][key]
     else:
         t = time.time()
         shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        path = os.path.join(shm, f"pb_bench_{os.environ.get('MASTER_PORT', '0')}_{cfg.cfg}_{n_docs}_{vocab}.img")
+        path = os.path.join(shm, f"pb_bench_{os.environ.get('MASTER_PORT', '0')}_{cfg.name}_{n_docs}_{vocab}.img")
         if rank == 0:
             ix = Index(cfg.n_fields, device=dev)
             wl.build_into(ix)
@@ -506,6 +506,13 @@ def run_config(ctx, cfg):
         "side_fold": {"kernel": f"pbk::binfold_kernel<F={F},{cfg.scorer}>", "ms": acc["ms_side_fold"], "rows": None,
                       "bytes_per_row": None, "launches": st["side_rounds"]},
     }
+    # rows of the single-list launch that streamed from the compact copy (u16 doc offsets: 2 B/row fewer)
+    rows_compact = int(st.get("rows_streamed_compact", 0))
+    if rows_compact and classes["direct"]["rows"]:
+        d = classes["direct"]
+        d["rows_compact"] = rows_compact
+        d["bytes_per_row"] = (d["rows"] * bpr - 2 * rows_compact) / d["rows"]
+        d["kernel"] += f" ({rows_compact / d['rows']:.1%} of the rows from the compact tiles, {bpr - 2} B/row)"
     for c in classes.values():
         c["share_of_step"] = c["ms"] / (dev_ms / args.steps) if dev_ms else None
         if c["rows"] and c["ms"] > 0:
@@ -526,7 +533,7 @@ def run_config(ctx, cfg):
     image_fits_l2 = lay["posting_bytes"] < 2 * L2_BYTES
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "class": dom_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "accounting": f"rows streamed by this launch class x {dom['bytes_per_row']} B/row of the device layout "
+                "accounting": f"rows streamed by this launch class x {dom['bytes_per_row']:.3g} B/row of the device layout "
                               f"/ its CUDA-event time (average launch of {max(dom['launches'], 1)})",
                 "bytes_per_row": dom["bytes_per_row"], "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_ms,
                 "share_of_step": dom["share_of_step"],
@@ -616,6 +623,7 @@ def run_config(ctx, cfg):
                 "stage_ms": {kk: acc[kk] for kk in ("ms_descend", "ms_plan", "ms_score", "ms_side", "ms_finalize", "ms_gather")},
                 "per_rank_ms": per_rank_ms,
                 "rows": {"scored_per_step": rows_all, "streamed_direct": st["rows_streamed_direct"],
+                         "streamed_compact": rows_compact,
                          "streamed_side": st["rows_streamed_side"], "streamed_union": st["rows_streamed_union"],
                          "union_queries": st["union_queries"], "diverted": st["rows_diverted"],
                          "legacy_records": st.get("legacy_records"), "results": res_all, "side_rounds": st["side_rounds"]},

@@ -298,6 +298,8 @@ typedef struct pb_batch_stats {
   uint64_t rows_streamed_side;  /* posting rows read by the class-G scoring launches (inside ms_side_score) */
   uint64_t rows_streamed_union; /* posting rows read by the union kernel */
   uint64_t union_queries;       /* queries answered by the union kernel */
+  uint64_t rows_streamed_compact; /* of rows_streamed_direct: rows read from the compact copy of the tiles (u16 doc offsets,
+                                     2 + 2F bytes per row instead of 4 + 2F; built for images that do not fit L2) */
 } pb_batch_stats;
 int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out);
 /* Stats of the last pb_query_batch / pb_query_full call on this index. */
@@ -379,7 +381,7 @@ const char* pb_version(void);
 PB_STATIC_ASSERT(sizeof(pb_index_image) == 248, "pb_index_image layout");
 PB_STATIC_ASSERT(sizeof(pb_query_batch_desc) == 72, "pb_query_batch_desc layout");
 PB_STATIC_ASSERT(sizeof(pb_query_results) == 48, "pb_query_results layout");
-PB_STATIC_ASSERT(sizeof(pb_batch_stats) == 160, "pb_batch_stats layout");
+PB_STATIC_ASSERT(sizeof(pb_batch_stats) == 168, "pb_batch_stats layout");
 PB_STATIC_ASSERT(sizeof(pb_builder_info) == 128, "pb_builder_info layout");
 PB_STATIC_ASSERT(sizeof(pb_doc_tokens) == 32, "pb_doc_tokens layout");
 

@@ -81,7 +81,7 @@ class BatchStats(C.Structure):
                 ("ms_finalize", C.c_float), ("score_launches", C.c_uint32), ("ms_gather", C.c_float),
                 ("ms_side_mark", C.c_float), ("ms_side_score", C.c_float), ("ms_side_fold", C.c_float),
                 ("ms_union", C.c_float), ("rows_streamed_side", C.c_uint64), ("rows_streamed_union", C.c_uint64),
-                ("union_queries", C.c_uint64)]
+                ("union_queries", C.c_uint64), ("rows_streamed_compact", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -135,6 +135,11 @@ struct pb_index {
   bool u_ok = false;
   bool u_warp = false;           // union_warp_kernel (small shards, one warp per task) instead of union_kernel (2048-doc shards per CTA)
   DBuf<ull> liverowcnt_prefix, dflive_prefix;   // per-term prefixes of term_live_rows / term_df_live (class-U row statistics)
+  // compact copy of the narrow tiles (IndexView::cpost): u16 doc offsets, streamed by the single-list launch
+  DBuf<uint32_t> cpost, cbase;
+  DBuf<uint8_t> term_compact;
+  bool compact = false;
+  uint64_t compact_rows = 0;     // rows of the lists that stream from the compact copy
   // host copies needed to rebuild term strings (pb_index_expand_term) and to recompute idf
   std::vector<uint32_t> h_node_parent, h_node_char, h_term_node;
   std::vector<uint64_t> h_term_row_begin, h_df_live, h_df_extra;
@@ -163,6 +168,7 @@ struct pb_index {
     v.term_row_begin = term_row_begin.p; v.term_byte_len = term_byte_len.p;
     v.post_blocks = post_blocks.p; v.tile_words = tile_words; v.narrow = narrow ? 1u : 0u;
     for (int f = 0; f < 4; ++f) v.fl_bits[f] = fl_bits[f];
+    v.cpost = compact ? cpost.p : nullptr; v.cbase = compact ? cbase.p : nullptr; v.term_compact = compact ? term_compact.p : nullptr;
     v.removed = removed.p;
     v.term_df_live = term_df_live.p; v.term_live_rows = term_live_rows.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
     v.term_idf = term_idf.p; v.eb = eb.p;
@@ -173,6 +179,44 @@ struct pb_index {
     return v;
   }
 };
+
+// Compact copy of the narrow tiles (IndexView::cpost), built on the device from the tiles already in
+// HBM.  It pays where the single-list stream is bound by HBM bandwidth, i.e. for images that do not fit L2; on an
+// L2-resident image the two extra instructions per row cost more than the bytes save (PB_POSTING_COMPACT=0|1 forces).
+static int index_build_compact(pb_index* ix) {
+  ix->compact = false;
+  ix->compact_rows = 0;
+  if (!ix->narrow || ix->n_rows < (uint64_t)TILE_ROWS || ix->n_terms == 0) return PB_OK;
+  const uint64_t tiles = ix->n_rows_padded / TILE_ROWS;
+  const uint64_t posting_bytes = tiles * (uint64_t)ix->tile_words * 4ull;
+  bool want = posting_bytes >= (256ull << 20);
+  if (const char* e = std::getenv("PB_POSTING_COMPACT")) {
+    if (!std::strcmp(e, "0")) want = false;
+    else if (!std::strcmp(e, "1")) want = true;
+  }
+  if (!want) return PB_OK;
+  const uint32_t CW = (TILE_ROWS / 2) * (1 + ix->F);
+  const uint64_t alloc_tiles = tiles + 2;                        // the streaming loop loads one tile ahead
+  CU(ix->cpost.ensure(alloc_tiles * CW + 64));                   // zero-filled
+  CU(ix->cbase.ensure(alloc_tiles + 2));
+  CU(ix->term_compact.ensure(ix->n_terms + 1));
+  DBuf<ull> d_rows;
+  CU(d_rows.ensure(1));
+  compact_tiles_kernel<<<ix->sm_count * 8, 256>>>(ix->post_blocks.p, ix->tile_words, ix->F, ix->n_rows / TILE_ROWS, alloc_tiles + 2,
+                                                  ix->cpost.p, ix->cbase.p);
+  CU(cudaGetLastError());
+  uint32_t min_tiles = 4;                                        // shorter lists are all edges and set-up anyway
+  if (const char* e = std::getenv("PB_COMPACT_MIN_TILES")) min_tiles = (uint32_t)std::max(1, atoi(e));   // tests
+  term_compact_kernel<<<ix->sm_count * 8, 256>>>(ix->term_row_begin.p, (uint32_t)ix->n_terms, ix->cbase.p, min_tiles,
+                                                 ix->term_compact.p, d_rows.p);
+  CU(cudaGetLastError());
+  ull h_rows = 0;
+  CU(cudaMemcpy(&h_rows, d_rows.p, sizeof(ull), cudaMemcpyDeviceToHost));
+  ix->compact_rows = h_rows;
+  ix->compact = h_rows > 0;
+  if (!ix->compact) { ix->cpost.release(); ix->cbase.release(); ix->term_compact.release(); }
+  return PB_OK;
+}
 
 // Builds the union image on the device from the term-major image already resident in HBM: a stable
 // radix sort of (doc shard, row) keeps the rows of a shard in (term, doc) order.
@@ -1096,6 +1140,7 @@ int batch_finish(pb_batch* b) {
   S.rows_streamed_union = h_stats[2 * ST_COUNT + ST_ROWS_STREAMED];
   S.rows_diverted = h_stats[ST_COUNT + ST_ROWS_DIVERTED];
   S.rows_streamed_direct = h_stats[ST_ROWS_STREAMED];
+  S.rows_streamed_compact = h_stats[ST_ROWS_COMPACT];
   S.results_emitted = h_full[1];
   S.gpu_launches = b->launches + (b->gather_pending ? 1u : 0u);
   float ms = 0;
@@ -1346,6 +1391,7 @@ static int index_create_impl(const pb_index_image* im, const pb::BuilderLogView*
         CU(upload(ix->post_blocks, nb.data(), nb.size(), 0));
       }
     }
+    RC(index_build_compact(ix));
     RC(index_build_union(ix));
     // rank directories of the dense lists (>= n_docs / 32 rows, capped at 1 GB): built on the device
     {

@@ -79,6 +79,17 @@ struct IndexView {
   const uint32_t* post_blocks;
   uint32_t tile_words;            // u32 words per tile: 128 (1 + 2F) wide, 128 + 64F narrow
   uint32_t narrow;
+  // Compact copy of the narrow tiles for the single-list stream (delta-coded doc ordinals): the doc
+  // column of a tile as u16 offsets from the tile's smallest doc, where that span fits 16 bits
+  //          [tile][doc - base u16 x128][code0 u16 x128]..[code(F-1) u16 x128]                   = 2 + 2F bytes / row
+  // same tile index as post_blocks (stride 64 (1 + F) words), `cbase[tile]` = the base or NONE (tile not compact);
+  // `term_compact[t]` = every interior tile of term t's list is compact, i.e. the list may be streamed from here.
+  // Built on the device at pb_index_create for images that do not fit L2 (PB_POSTING_COMPACT); null otherwise.
+  // Only the streaming loop of class S reads it: marking, directories, the union image and random access keep
+  // reading post_blocks.
+  const uint32_t* cpost;
+  const uint32_t* cbase;
+  const uint8_t* term_compact;
   uint32_t fl_bits[4];
   const uint32_t* removed;        // bitmap, bit set = doc not live
   const uint64_t* term_df_live;
@@ -148,7 +159,7 @@ struct Outputs {
   unsigned long long* results_total;   // sum of n_results over the batch
 };
 
-enum StatSlot { ST_ROWS_STREAMED = 0, ST_ROWS_SCORED, ST_POINTER_VISITS, ST_ROWS_DIVERTED, ST_COUNT };
+enum StatSlot { ST_ROWS_STREAMED = 0, ST_ROWS_SCORED, ST_POINTER_VISITS, ST_ROWS_DIVERTED, ST_ROWS_COMPACT, ST_COUNT };
 
 struct ScoreParams {
   IndexView ix;
@@ -984,6 +995,48 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
   }
 }
 
+// Interior tiles of a single-list segment whose term is compact (IndexView::cpost): 2 + 2F bytes per row instead of
+// 4 + 2F.  Same pipeline as above (tile i + 1 in flight while tile i is scored, L2 prefetch further ahead); the doc
+// ordinals are rebuilt as base + u16 (two instructions per row) and the tile is scored by the same compute_tile.
+template <int F> struct CompactRegs { uint2 d16; uint32_t base; uint2 cq[F]; };
+template <int F>
+__device__ __forceinline__ void load_compact(const uint32_t* cb, const uint32_t* bp, int lane, CompactRegs<F>& R) {
+  R.d16 = ldg_stream_u64(cb + lane * 2);
+#pragma unroll
+  for (int f = 0; f < F; ++f) R.cq[f] = ldg_stream_u64(cb + (TILE_ROWS / 2) * (1 + f) + lane * 2);
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(R.base) : "l"(bp));      // one address per warp: a broadcast
+}
+template <int F, int SCORER, int SIMPLE>
+__device__ __forceinline__ void interior_tiles_compact(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
+                                                       uint64_t tile_row, uint32_t n_tiles, int lane, WarpAcc& acc,
+                                                       uint32_t& st_div) {
+  if (n_tiles == 0) return;
+  constexpr uint32_t CW = (TILE_ROWS / 2) * (1 + F);          // u32 words per compact tile
+  const uint32_t* cb = P.ix.cpost + (tile_row / TILE_ROWS) * (uint64_t)CW;
+  const uint32_t* bp = P.ix.cbase + tile_row / TILE_ROWS;
+  CompactRegs<F> cur;
+  load_compact<F>(cb, bp, lane, cur);
+#pragma unroll 2
+  for (uint32_t i = 0; i < n_tiles; ++i) {
+    CompactRegs<F> nxt;
+    load_compact<F>(cb + CW, bp + 1, lane, nxt);               // the spare tiles behind the image make this safe
+#if PB_L2_AHEAD
+    if (P.l2_prefetch && i + PB_L2_AHEAD < n_tiles && lane < (int)(CW / 32))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(cb + PB_L2_AHEAD * CW + lane * 32));
+#endif
+    TileRegs<F, true> R;
+    R.mw = 0;
+    R.dq = make_uint4(cur.base + (cur.d16.x & 0xFFFFu), cur.base + (cur.d16.x >> 16),
+                      cur.base + (cur.d16.y & 0xFFFFu), cur.base + (cur.d16.y >> 16));
+#pragma unroll
+    for (int f = 0; f < F; ++f) R.cq[f] = cur.cq[f];
+    compute_tile<F, SCORER, false, false, true, SIMPLE, true>(P, s_tab, C, R, 0, 0u, lane, acc, st_div);
+    cur = nxt;
+    cb += CW;
+    ++bp;
+  }
+}
+
 // CTA shape of the scoring kernel: no barrier after the table is loaded, so a CTA is just a bag of
 // warps.  The host picks (threads per CTA, CTAs per SM) so that 24 warps are resident per SM
 // whatever the shared-memory table costs: 3 x 256, 2 x 384 or 1 x 768 threads (80 registers per thread;
@@ -1066,7 +1119,13 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 1) score_kernel(const __gri
       {
         const uint64_t row = (abs0 + (t - st0)) * TILE_ROWS;
         const uint32_t n = (uint32_t)(ib - t);
-        if (fast) {
+        if (!GMODE && NARROW && fast && P.ix.cpost != nullptr && P.ix.term_compact[sg.term]) {
+          if constexpr (!GMODE && NARROW) {
+            if (simple) interior_tiles_compact<F, SCORER, 2>(P, s_tab, C, row, n, lane, acc, st_div);
+            else if (P.boosts_all_one) interior_tiles_compact<F, SCORER, 1>(P, s_tab, C, row, n, lane, acc, st_div);
+            else interior_tiles_compact<F, SCORER, 0>(P, s_tab, C, row, n, lane, acc, st_div);
+          }
+        } else if (fast) {
           if (simple) interior_tiles<F, SCORER, GMODE, true, 2, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
           else if (P.boosts_all_one) interior_tiles<F, SCORER, GMODE, true, 1, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
           else interior_tiles<F, SCORER, GMODE, true, 0, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);

@@ -132,7 +132,7 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
     s_tiles[n_queries] = 0ull; qt_gcount[n_qterms] = 0ull;
     if (up.q_isu) { up.q_isu[n_queries] = 0ull; up.q_isu2[n_queries] = 0ull; }
   }
-  unsigned long long st_rows = 0, st_live = 0, st_ptr = 0;
+  unsigned long long st_rows = 0, st_live = 0, st_ptr = 0, st_compact = 0;
   unsigned long long su_rows = 0, su_live = 0, su_ptr = 0;
   if (q < n_queries) {
   uint64_t t0 = query_term_off[q], t1 = query_term_off[q + 1];
@@ -161,6 +161,10 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
     st_rows = b - a;                       // rows streamed
     st_live = ix.term_live_rows[term];     // rows whose doc is live = score() evaluations
     st_ptr = ix.term_df_live[term];        // reference DocumentPointer visits (sum of multiplicities)
+    if (ix.cpost != nullptr && ix.term_compact[term]) {    // rows of the interior tiles stream from the compact copy
+      const uint64_t i0 = (a + TILE_ROWS - 1) / TILE_ROWS, i1 = b / TILE_ROWS;
+      if (i1 > i0) st_compact = (i1 - i0) * TILE_ROWS;
+    }
   }
   seg_s[q] = s;
   s_tiles[q] = tiles;
@@ -209,7 +213,9 @@ __global__ void plan_query_kernel(IndexView ix, uint64_t n_queries,
     qt_gcount[t] = g ? (unsigned long long)(ix.live_prefix[qt_hi[t]] - ix.live_prefix[qt_lo[t]]) : 0ull;
   }
   st_rows = warp_sum_u64(st_rows); st_live = warp_sum_u64(st_live); st_ptr = warp_sum_u64(st_ptr);
+  st_compact = warp_sum_u64(st_compact);
   if ((threadIdx.x & 31) == 0 && st_rows) {
+    if (st_compact) atomicAdd(&stats[ST_ROWS_COMPACT], st_compact);
     atomicAdd(&stats[ST_ROWS_STREAMED], st_rows);
     atomicAdd(&stats[ST_ROWS_SCORED], st_live);
     atomicAdd(&stats[ST_POINTER_VISITS], st_ptr);
@@ -461,6 +467,60 @@ __global__ void __launch_bounds__(CTA_THREADS) finalize_kernel(Outputs o, uint64
       o.topk_score[(size_t)q * o.k + lane] = acc.ts;
     }
     if (lane == 0) o.topk_n[q] = ntop;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Compact copy of the narrow tiles (IndexView::cpost): one warp per FULL tile.  A tile whose docs span less than
+// 2^16 gets its doc column as u16 offsets from the tile's smallest doc, its code columns copied behind, and its
+// base in cbase[tile]; any other tile gets cbase = NONE and its block is left zero.
+// ------------------------------------------------------------------------------------------
+__global__ void compact_tiles_kernel(const uint32_t* __restrict__ post, uint32_t tile_words, uint32_t F, uint64_t n_full_tiles,
+                                     uint64_t n_tiles_alloc, uint32_t* __restrict__ cpost, uint32_t* __restrict__ cbase) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t CW = (TILE_ROWS / 2) * (1 + F);
+  for (uint64_t t = w; t < n_tiles_alloc; t += W) {
+    if (t >= n_full_tiles) { if (lane == 0) cbase[t] = NONE; continue; }
+    const uint32_t* src = post + t * (uint64_t)tile_words;
+    const uint4 d = *reinterpret_cast<const uint4*>(src + lane * 4);
+    uint32_t lo = min(min(d.x, d.y), min(d.z, d.w)), hi = max(max(d.x, d.y), max(d.z, d.w));
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, of));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, of));
+    }
+    const bool fit = hi - lo < 65536u;
+    if (lane == 0) cbase[t] = fit ? lo : NONE;
+    if (!fit) continue;
+    uint32_t* dst = cpost + t * (uint64_t)CW;
+    *reinterpret_cast<uint2*>(dst + lane * 2) = make_uint2((d.x - lo) | ((d.y - lo) << 16), (d.z - lo) | ((d.w - lo) << 16));
+    for (uint32_t f = 0; f < F; ++f)
+      *reinterpret_cast<uint2*>(dst + (TILE_ROWS / 2) * (1 + f) + lane * 2) =
+          *reinterpret_cast<const uint2*>(src + TILE_ROWS + f * (TILE_ROWS / 2) + lane * 2);
+  }
+}
+
+// term_compact[t] = the list has at least `min_tiles` interior tiles and every one of them is compact.  One warp per term.
+__global__ void term_compact_kernel(const uint64_t* __restrict__ term_row_begin, uint32_t n_terms, const uint32_t* __restrict__ cbase,
+                                    uint32_t min_tiles, uint8_t* __restrict__ term_compact, unsigned long long* __restrict__ rows_compact) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = w; t < n_terms; t += W) {
+    const uint64_t a = term_row_begin[t], b = term_row_begin[t + 1];
+    const uint64_t i0 = (a + TILE_ROWS - 1) / TILE_ROWS, i1 = b / TILE_ROWS;
+    bool ok = i1 >= i0 + min_tiles;
+    if (ok) {
+      bool bad = false;
+      for (uint64_t i = i0 + lane; i < i1; i += 32) bad = bad || cbase[i] == NONE;
+      ok = !__any_sync(0xffffffffu, bad);
+    }
+    if (lane == 0) {
+      term_compact[t] = ok ? 1 : 0;
+      if (ok) atomicAdd(rows_compact, (unsigned long long)((i1 - i0) * TILE_ROWS));
+    }
   }
 }
 
