@@ -299,7 +299,7 @@ typedef struct pb_batch_stats {
   uint64_t rows_streamed_union; /* posting rows read by the union kernel */
   uint64_t union_queries;       /* queries answered by the union kernel */
   uint64_t rows_streamed_compact; /* of rows_streamed_direct: rows read from the compact copy of the tiles (u16 doc offsets,
-                                     2 + 2F bytes per row instead of 4 + 2F; built for images that do not fit L2) */
+                                     2 + 2F bytes per row instead of 4 + 2F; built only with PB_POSTING_COMPACT=1) */
 } pb_batch_stats;
 int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out);
 /* Stats of the last pb_query_batch / pb_query_full call on this index. */

@@ -181,20 +181,17 @@ struct pb_index {
 };
 
 // Compact copy of the narrow tiles (IndexView::cpost), built on the device from the tiles already in
-// HBM.  It pays where the single-list stream is bound by HBM bandwidth, i.e. for images that do not fit L2; on an
-// L2-resident image the two extra instructions per row cost more than the bytes save (PB_POSTING_COMPACT=0|1 forces).
+// HBM — only on request (PB_POSTING_COMPACT=1).  Measured on B200 ("what was tried"): the single-list
+// stream reads 25 % fewer bytes from it and is 5-6 % SLOWER, on the 2.1 GB image of cfg 3/4 as on the L2-resident
+// one of cfg 1: the stream is bound by instruction issue / dependent-issue latency, and rebuilding the doc ordinals
+// costs two instructions per row.  Kept as a tested layout for bandwidth-starved parts, not used by default.
 static int index_build_compact(pb_index* ix) {
   ix->compact = false;
   ix->compact_rows = 0;
   if (!ix->narrow || ix->n_rows < (uint64_t)TILE_ROWS || ix->n_terms == 0) return PB_OK;
   const uint64_t tiles = ix->n_rows_padded / TILE_ROWS;
-  const uint64_t posting_bytes = tiles * (uint64_t)ix->tile_words * 4ull;
-  bool want = posting_bytes >= (256ull << 20);
-  if (const char* e = std::getenv("PB_POSTING_COMPACT")) {
-    if (!std::strcmp(e, "0")) want = false;
-    else if (!std::strcmp(e, "1")) want = true;
-  }
-  if (!want) return PB_OK;
+  const char* e = std::getenv("PB_POSTING_COMPACT");
+  if (!(e && !std::strcmp(e, "1"))) return PB_OK;
   const uint32_t CW = (TILE_ROWS / 2) * (1 + ix->F);
   const uint64_t alloc_tiles = tiles + 2;                        // the streaming loop loads one tile ahead
   CU(ix->cpost.ensure(alloc_tiles * CW + 64));                   // zero-filled

@@ -1,5 +1,6 @@
 """-m gpu: the compact copy of the tiles (u16 doc offsets; IndexView::cpost in csrc/kernels.cuh) that the
-single-list launch streams on images larger than L2.  PB_POSTING_COMPACT=1 builds it for small corpora too and
+single-list launch can stream instead of the u32 doc column.  PB_POSTING_COMPACT=1 builds it (off by default: measured
+slower on B200 although it reads fewer bytes) and
 PB_COMPACT_MIN_TILES=1 lets every list with one interior tile use it; the results must equal the oracle's, bit for bit,
 and those of the same index without the copy.  The stats say how many rows really streamed from it."""
 import numpy as np
@@ -91,7 +92,7 @@ def test_compact_tiles_with_non_unit_boosts_and_full_results(monkeypatch):
         H.assert_same_results([(int(d), float(s)) for d, s in zip(docs[sel], scores[sel])], e, ctx=f"q={q}")
 
 
-def test_small_images_do_not_build_the_copy_by_default():
+def test_the_copy_is_not_built_by_default():
     cfg = W.CONFIGS["cfg1"]
     wl = W.Workload(cfg, n_docs=20_000, vocab=1 << 10)
     ix = Index(cfg.n_fields)
