@@ -135,6 +135,8 @@ struct pb_index {
   bool u_ok = false;
   bool u_warp = false;           // union_warp_kernel (small shards, one warp per task) instead of union_kernel (2048-doc shards per CTA)
   DBuf<ull> liverowcnt_prefix, dflive_prefix;   // per-term prefixes of term_live_rows / term_df_live (class-U row statistics)
+  DBuf<uint32_t> row_dead;       // IndexView::row_dead: the removed bitmap per posting row (rebuilt with the live state)
+  bool row_dead_ok = false;
   // compact copy of the narrow tiles (IndexView::cpost): u16 doc offsets, streamed by the single-list launch
   DBuf<uint32_t> cpost, cbase;
   DBuf<uint8_t> term_compact;
@@ -170,6 +172,7 @@ struct pb_index {
     for (int f = 0; f < 4; ++f) v.fl_bits[f] = fl_bits[f];
     v.cpost = compact ? cpost.p : nullptr; v.cbase = compact ? cbase.p : nullptr; v.term_compact = compact ? term_compact.p : nullptr;
     v.removed = removed.p;
+    v.row_dead = (n_removed && row_dead_ok) ? row_dead.p : nullptr;
     v.term_df_live = term_df_live.p; v.term_live_rows = term_live_rows.p; v.live_prefix = live_prefix.p; v.liverows_prefix = liverows_prefix.p;
     v.term_idf = term_idf.p; v.eb = eb.p;
     v.dir = dir.p; v.term_dir = term_dir.p; v.dir_words = dir_words;
@@ -294,6 +297,19 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
   ix->n_removed = n_removed;
   ix->n_live = n_live;
   ++ix->live_epoch;
+  // the same bitmap per posting row, for the scoring loop (PB_ROW_DEAD=0: keep probing the doc bitmap - A/B and tests)
+  ix->row_dead_ok = false;
+  if (n_removed && ix->n_rows) {
+    const char* e = std::getenv("PB_ROW_DEAD");
+    if (!(e && !std::strcmp(e, "0"))) {
+      const uint64_t tiles = ix->n_rows_padded / TILE_ROWS;
+      CU(ix->row_dead.ensure((tiles + 3) * 4));                  // zero-filled; + the look-ahead tiles
+      row_dead_kernel<<<ix->sm_count * 8, 256>>>(ix->post_blocks.p, ix->tile_words, tiles, ix->removed.p, (uint32_t)ix->n_docs, ix->row_dead.p);
+      CU(cudaGetLastError());
+      CU(cudaDeviceSynchronize());
+      ix->row_dead_ok = true;
+    }
+  }
   for (uint32_t f = 0; f < ix->F; ++f) ix->avg[f] = avg[f];
   const size_t NT = ix->n_terms;
   CU(ix->term_df_live.ensure(NT + 1));

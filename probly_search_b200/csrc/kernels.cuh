@@ -93,6 +93,10 @@ struct IndexView {
   const uint8_t* term_compact;
   uint32_t fl_bits[4];
   const uint32_t* removed;        // bitmap, bit set = doc not live
+  // The same fact per posting ROW (bit r % 128 of the 4 words of tile r / 128; rebuilt by pb_index_set_live_state when
+  // docs are removed, null while none is): the scoring loop takes this lane's word with the tile - one load whose
+  // address does not depend on posting data - instead of four dependent probes of `removed` per lane and tile.
+  const uint32_t* row_dead;
   const uint64_t* term_df_live;
   const uint32_t* term_live_rows; // rows of the term whose doc is live
   const uint32_t* live_prefix;    // [n_terms+1] number of terms with df_live > 0 before t
@@ -659,6 +663,7 @@ template <int F> struct TileRegs<F, false> {
   uint4 dq;
   uint4 tq[F], lq[F];
   uint32_t mw;      // GMODE primary list: the row-mask word holding this lane's 4 bits
+  uint32_t dw;      // IndexView::row_dead word holding this lane's 4 bits (0 when no doc is removed)
   __device__ __forceinline__ uint32_t tf(const IndexView&, int f, int j) const { return u4c(tq[f], j); }
   __device__ __forceinline__ uint32_t fl(const IndexView&, int f, int j) const { return u4c(lq[f], j); }
   // index into field f's table of saturated tf (row stride flcap)
@@ -668,6 +673,7 @@ template <int F> struct TileRegs<F, true> {
   uint4 dq;
   uint2 cq[F];
   uint32_t mw;
+  uint32_t dw;
   __device__ __forceinline__ uint32_t code(int f, int j) const {       // one PRMT
     return __byte_perm(j < 2 ? cq[f].x : cq[f].y, 0u, (j & 1) ? 0x4432u : 0x4410u);
   }
@@ -814,10 +820,20 @@ template <int F, bool NARROW>
 __device__ __forceinline__ const uint32_t* tile_base(const ScoreParams& P, uint64_t tile_row) {
   return P.ix.post_blocks + (tile_row / TILE_ROWS) * (uint64_t)TileGeom<F, NARROW>::WORDS;
 }
+__device__ __forceinline__ uint32_t ld_dead(const uint32_t* p) {
+  uint32_t v = 0;
+  if (p != nullptr) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ const uint32_t* dead_word(const IndexView& ix, uint64_t tile_row, int lane) {
+  return ix.row_dead != nullptr ? ix.row_dead + (tile_row / TILE_ROWS) * 4 + (lane >> 3) : nullptr;
+}
 template <int F, bool GMODE, bool NARROW>
-__device__ __forceinline__ void load_tile(const SegCtx& C, const uint32_t* base, const uint32_t* maskp, int lane, TileRegs<F, NARROW>& R) {
+__device__ __forceinline__ void load_tile(const SegCtx& C, const uint32_t* base, const uint32_t* maskp, int lane, TileRegs<F, NARROW>& R,
+                                          const uint32_t* deadp = nullptr) {
   // one contiguous block per tile: a single base address, immediate column offsets
   R.mw = 0;
+  R.dw = ld_dead(deadp);
   if (GMODE && maskp != nullptr) {
     // the address does not depend on posting data: the mask word travels together with the tile
     // (maskp is null when the tile summary says the tile diverts nothing)
@@ -827,7 +843,8 @@ __device__ __forceinline__ void load_tile(const SegCtx& C, const uint32_t* base,
   load_cols(R, base, lane);
 }
 
-template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE, bool NARROW>
+// DEAD: the tile's removed-row bits came with the tile (R.dw, IndexView::row_dead) - no probe of the doc bitmap
+template <int F, int SCORER, bool GMODE, bool EDGE, bool FAST, int SIMPLE, bool NARROW, bool DEAD = false>
 __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                              const TileRegs<F, NARROW>& R, uint64_t tile_row, uint32_t ti, int lane,
                                              WarpAcc& acc, uint32_t& st_div) {
@@ -844,7 +861,9 @@ __device__ __forceinline__ void compute_tile(const ScoreParams& P, const uint32_
       valid |= (r >= lo && r < hi) ? (1u << j) : 0u;
     }
   }
-  if (P.ix.has_removed) {               // removed-but-not-vacuumed docs are skipped (query.rs:65)
+  if (DEAD) {                           // removed-but-not-vacuumed docs are skipped (query.rs:65)
+    valid &= ~((R.dw >> ((lane & 7) * 4)) & 0xFu);
+  } else if (P.ix.has_removed) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (((valid >> j) & 1u) && ((__ldg(&P.ix.removed[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) valid &= ~(1u << j);
@@ -945,7 +964,7 @@ __device__ __forceinline__ void process_tile(const ScoreParams& P, const uint32_
 // (Round 3 tried a compile-time PRIMARY specialisation of this loop — no mask code at all for non-primary segments,
 // no run-time flag for primary ones: class-G launch 18.4 ms instead of 15.6 in an alternating A/B on one box.  The
 // shared loop below stays.)
-template <int F, int SCORER, bool GMODE, bool FAST, int SIMPLE, bool NARROW>
+template <int F, int SCORER, bool GMODE, bool FAST, int SIMPLE, bool NARROW, bool DEAD = false>
 __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint32_t s_tab, const SegCtx& C,
                                                uint64_t tile_row, uint32_t n_tiles, int lane, WarpAcc& acc,
                                                uint32_t& st_div) {
@@ -962,14 +981,17 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
       if (primary) asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
       return v;
     };
+    // DEAD: the row_dead words travel with the tiles (the spare tiles behind the image cover the look-ahead)
+    const uint32_t* deadp = DEAD ? dead_word(P.ix, tile_row, lane) : nullptr;
     TileRegs<F, NARROW> cur;
-    load_tile<F, GMODE, NARROW>(C, base, nullptr, lane, cur);
+    load_tile<F, GMODE, NARROW>(C, base, nullptr, lane, cur, deadp);
     cur.mw = ld_mask(maskp);
     uint32_t mw1 = ld_mask(maskp + 4);               // mask of tile i + 1
 #pragma unroll 2
     for (uint32_t i = 0; i < n_tiles; ++i) {
       TileRegs<F, NARROW> nxt;
-      load_tile<F, GMODE, NARROW>(C, base + TileGeom<F, NARROW>::WORDS, nullptr, lane, nxt);
+      if (DEAD) deadp += 4;
+      load_tile<F, GMODE, NARROW>(C, base + TileGeom<F, NARROW>::WORDS, nullptr, lane, nxt, deadp);
 #if PB_L2_AHEAD
       // an image larger than L2 (cfg 3/4: 2.1 GB) streams from HBM: one tile of register look-ahead does
       // not cover DRAM latency, so the lines of the tile PB_L2_AHEAD tiles further on are pulled into L2
@@ -980,9 +1002,9 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
       // a primary-list tile whose row-mask bits are all clear diverts nothing: score it exactly like a
       // single-list tile (the common case: ~93 % of the tiles of the cfg 1 batch)
       if (primary && !__any_sync(0xffffffffu, cur.mw != 0u))
-        compute_tile<F, SCORER, false, false, FAST, SIMPLE, NARROW>(P, s_tab, C, cur, 0, 0u, lane, acc, st_div);
+        compute_tile<F, SCORER, false, false, FAST, SIMPLE, NARROW, DEAD>(P, s_tab, C, cur, 0, 0u, lane, acc, st_div);
       else
-        compute_tile<F, SCORER, GMODE, false, FAST, SIMPLE, NARROW>(P, s_tab, C, cur, 0, ti, lane, acc, st_div);
+        compute_tile<F, SCORER, GMODE, false, FAST, SIMPLE, NARROW, DEAD>(P, s_tab, C, cur, 0, ti, lane, acc, st_div);
       cur = nxt;
       cur.mw = mw1;
       mw1 = mw2;
@@ -999,9 +1021,10 @@ __device__ __forceinline__ void interior_tiles(const ScoreParams& P, const uint3
 // Interior tiles of a single-list segment whose term is compact (IndexView::cpost): 2 + 2F bytes per row instead of
 // 4 + 2F.  Same pipeline as above (tile i + 1 in flight while tile i is scored, L2 prefetch further ahead); the doc
 // ordinals are rebuilt as base + u16 (two instructions per row) and the tile is scored by the same compute_tile.
-template <int F> struct CompactRegs { uint2 d16; uint32_t base; uint2 cq[F]; };
+template <int F> struct CompactRegs { uint2 d16; uint32_t base; uint32_t dw; uint2 cq[F]; };
 template <int F>
-__device__ __forceinline__ void load_compact(const uint32_t* cb, const uint32_t* bp, int lane, CompactRegs<F>& R) {
+__device__ __forceinline__ void load_compact(const uint32_t* cb, const uint32_t* bp, const uint32_t* deadp, int lane, CompactRegs<F>& R) {
+  R.dw = ld_dead(deadp);
   R.d16 = ldg_stream_u64(cb + lane * 2);
 #pragma unroll
   for (int f = 0; f < F; ++f) R.cq[f] = ldg_stream_u64(cb + (TILE_ROWS / 2) * (1 + f) + lane * 2);
@@ -1015,23 +1038,27 @@ __device__ __forceinline__ void interior_tiles_compact(const ScoreParams& P, con
   constexpr uint32_t CW = (TILE_ROWS / 2) * (1 + F);          // u32 words per compact tile
   const uint32_t* cb = P.ix.cpost + (tile_row / TILE_ROWS) * (uint64_t)CW;
   const uint32_t* bp = P.ix.cbase + tile_row / TILE_ROWS;
+  const uint32_t* deadp = dead_word(P.ix, tile_row, lane);
   CompactRegs<F> cur;
-  load_compact<F>(cb, bp, lane, cur);
+  load_compact<F>(cb, bp, deadp, lane, cur);
 #pragma unroll 2
   for (uint32_t i = 0; i < n_tiles; ++i) {
     CompactRegs<F> nxt;
-    load_compact<F>(cb + CW, bp + 1, lane, nxt);               // the spare tiles behind the image make this safe
+    if (deadp != nullptr) deadp += 4;
+    load_compact<F>(cb + CW, bp + 1, deadp, lane, nxt);        // the spare tiles behind the image make this safe
 #if PB_L2_AHEAD
     if (P.l2_prefetch && i + PB_L2_AHEAD < n_tiles && lane < (int)(CW / 32))
       asm volatile("prefetch.global.L2 [%0];" ::"l"(cb + PB_L2_AHEAD * CW + lane * 32));
 #endif
     TileRegs<F, true> R;
     R.mw = 0;
+    R.dw = cur.dw;
     R.dq = make_uint4(cur.base + (cur.d16.x & 0xFFFFu), cur.base + (cur.d16.x >> 16),
                       cur.base + (cur.d16.y & 0xFFFFu), cur.base + (cur.d16.y >> 16));
 #pragma unroll
     for (int f = 0; f < F; ++f) R.cq[f] = cur.cq[f];
-    compute_tile<F, SCORER, false, false, true, SIMPLE, true>(P, s_tab, C, R, 0, 0u, lane, acc, st_div);
+    if (deadp != nullptr) compute_tile<F, SCORER, false, false, true, SIMPLE, true, true>(P, s_tab, C, R, 0, 0u, lane, acc, st_div);
+    else compute_tile<F, SCORER, false, false, true, SIMPLE, true, false>(P, s_tab, C, R, 0, 0u, lane, acc, st_div);
     cur = nxt;
     cb += CW;
     ++bp;
@@ -1126,6 +1153,10 @@ __global__ void __launch_bounds__(SCORE_MAX_THREADS, 1) score_kernel(const __gri
             else if (P.boosts_all_one) interior_tiles_compact<F, SCORER, 1>(P, s_tab, C, row, n, lane, acc, st_div);
             else interior_tiles_compact<F, SCORER, 0>(P, s_tab, C, row, n, lane, acc, st_div);
           }
+        } else if (fast && NARROW && P.ix.row_dead != nullptr) {      // docs are removed: their row bits come with the tiles
+          if (simple) interior_tiles<F, SCORER, GMODE, true, 2, NARROW, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
+          else if (P.boosts_all_one) interior_tiles<F, SCORER, GMODE, true, 1, NARROW, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
+          else interior_tiles<F, SCORER, GMODE, true, 0, NARROW, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
         } else if (fast) {
           if (simple) interior_tiles<F, SCORER, GMODE, true, 2, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);
           else if (P.boosts_all_one) interior_tiles<F, SCORER, GMODE, true, 1, NARROW>(P, s_tab, C, row, n, lane, acc, st_div);

@@ -502,6 +502,28 @@ __global__ void compact_tiles_kernel(const uint32_t* __restrict__ post, uint32_t
   }
 }
 
+// IndexView::row_dead: bit r % 128 of tile r / 128 = the doc of posting row r is removed.  One warp per tile (the pad rows of
+// the last tile read doc 0: whatever they get is never used, the scoring loop masks rows outside a list).
+__global__ void row_dead_kernel(const uint32_t* __restrict__ post, uint32_t tile_words, uint64_t n_tiles,
+                                const uint32_t* __restrict__ removed, uint32_t n_docs, uint32_t* __restrict__ row_dead) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t W = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = w; t < n_tiles; t += W) {
+    const uint4 d = *reinterpret_cast<const uint4*>(post + t * (uint64_t)tile_words + lane * 4);
+    const uint32_t dv[4] = {d.x, d.y, d.z, d.w};
+    uint32_t nib = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (dv[j] < n_docs && ((__ldg(&removed[dv[j] >> 5]) >> (dv[j] & 31)) & 1u)) nib |= 1u << j;
+    uint32_t word = nib << ((lane & 7) * 4);
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    word |= __shfl_xor_sync(0xffffffffu, word, 4);
+    if ((lane & 7) == 0) row_dead[t * 4 + (lane >> 3)] = word;
+  }
+}
+
 // term_compact[t] = the list has at least `min_tiles` interior tiles and every one of them is compact.  One warp per term.
 __global__ void term_compact_kernel(const uint64_t* __restrict__ term_row_begin, uint32_t n_terms, const uint32_t* __restrict__ cbase,
                                     uint32_t min_tiles, uint8_t* __restrict__ term_compact, unsigned long long* __restrict__ rows_compact) {

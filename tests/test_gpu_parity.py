@@ -152,6 +152,40 @@ def test_scaled_configs_match_oracle(cfg_name, n_docs, vocab, n_queries, removed
     np.testing.assert_array_equal(again.topk_doc, got.topk_doc)
 
 
+@pytest.mark.parametrize("row_dead", ["1", "0"])
+@pytest.mark.parametrize("cfg_name,removed_cfg", [("cfg4", "cfg4"), ("cfg2", "cfg4"), ("cfg1", "cfg4")])
+def test_removed_docs_by_row_bits_and_by_bitmap_probe(monkeypatch, row_dead, cfg_name, removed_cfg):
+    """Removed-but-not-vacuumed docs (query.rs:65): the scoring loop reads their bits per posting ROW with the tile
+    (IndexView::row_dead, default) or probes the doc bitmap (PB_ROW_DEAD=0; edge tiles and the wide layout always do).
+    Both must give the oracle's answers; a second set_live_state (more removals) must rebuild the row bits."""
+    monkeypatch.setenv("PB_ROW_DEAD", row_dead)
+    cfg = W.CONFIGS[cfg_name]
+    n_docs, vocab = 60_000, 1 << 11
+    wl = W.Workload(cfg, n_docs=n_docs, vocab=vocab)
+    ix, o = Index(cfg.n_fields), orc.OracleIndex(cfg.n_fields)
+    wl.build_into(ix)
+    wl.build_into(o)
+    fq = wl.queries(120)
+    scorer = orc.BM25 if cfg.scorer == "bm25" else orc.ZERO_TO_ONE
+    gone = W.Workload(W.CONFIGS[removed_cfg], n_docs=n_docs, vocab=vocab).removed_ordinals()
+    k = 10
+    for part in (gone[: len(gone) // 2], gone[len(gone) // 2:]):
+        for d in part:
+            ix.remove_document(int(d))
+            o.remove_document(int(d))
+        got = ix.query_batch_flat(fq, CALC[scorer](), cfg.boosts, k)
+        exp = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, scorer, cfg.boosts, k)
+        np.testing.assert_array_equal(got.n_results, exp["n_results"])
+        np.testing.assert_array_equal(got.doc_digest, exp["doc_digest"])
+        np.testing.assert_array_equal(got.score_digest, exp["score_digest"])
+        np.testing.assert_array_equal(got.topk_n, exp["topk_n"])
+        for q in range(fq.n_queries):
+            n = int(got.topk_n[q])
+            np.testing.assert_array_equal(got.topk_doc[q, :n], exp["topk_key"][q, :n].astype(np.uint32))
+            np.testing.assert_array_equal(got.topk_score[q, :n], exp["topk_score"][q, :n])
+        assert ix.last_stats()["pointer_visits"] == exp["score_calls"]
+
+
 def test_full_results_sample_matches_oracle():
     cfg, ix, o, fq, scorer = _scaled("cfg1", 30_000, 1 << 12, 40)
     qi, docs, scores = ix.query_full_flat(fq, CALC[scorer](), cfg.boosts)
