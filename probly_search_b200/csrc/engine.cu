@@ -404,6 +404,7 @@ struct pb_batch {
   size_t h_stage_bytes = 0;
   bool tab_valid = false;      // the BM25 table on the device matches (tab_k1, tab_b, tab_epoch)
   double tab_k1 = 0, tab_b = 0;
+  double tab_scale[4] = {1.0, 1.0, 1.0, 1.0};   // power-of-two boosts folded into the resident table (ScoreParams::tab_scale)
   DBuf<UQuery> uq;
   DBuf<ull> q_isu, q_uidx, q_isu2, q_uidx2;
   DBuf<uint32_t> u_list, u_list2;
@@ -509,8 +510,25 @@ double bm25_tf_host(double k1, double b, double avg, uint32_t tf, uint32_t fl) {
   return ((k1 + 1.0) * tfd) / (k1 * ((1.0 - b) + b * ((double)fl / avg)) + tfd);
 }
 
+// The factor the table of field f is built with: the field's boost when it is +-2^k with a small exponent (exact, see
+// ScoreParams::tab_scale), else 1.0.  PB_FOLD_BOOST=0 keeps the multiplication in the loop (A/B, tests).
+double boost_fold(double boost) {
+  const char* e = std::getenv("PB_FOLD_BOOST");
+  const bool off = e && !std::strcmp(e, "0");
+  if (off || !std::isfinite(boost) || boost == 0.0 || boost == 1.0) return 1.0;
+  int ex = 0;
+  const double m = std::frexp(std::fabs(boost), &ex);
+  return (m == 0.5 && ex >= -30 && ex <= 31) ? boost : 1.0;
+}
+bool batch_table_current(const pb_batch* b) {
+  if (!(b->tab_valid && b->tab_k1 == b->k1 && b->tab_b == b->b && b->tab_epoch == b->ix->live_epoch)) return false;
+  for (uint32_t f = 0; f < b->ix->F; ++f) if (b->tab_scale[f] != boost_fold(b->boost[f])) return false;
+  return true;
+}
+
 int batch_build_table(pb_batch* b) {
   pb_index* ix = b->ix;
+  for (uint32_t f = 0; f < 4; ++f) b->tab_scale[f] = f < ix->F ? boost_fold(b->boost[f]) : 1.0;
   // (tf, fl) -> saturated tf, per field, tf-major with row stride flc.  In the narrow layout the row
   // stride is 1 << fl_bits so that a posting code indexes the table directly; the table may then only
   // be cut along tf.
@@ -534,7 +552,7 @@ int batch_build_table(pb_batch* b) {
   for (uint32_t f = 0; f < ix->F; ++f) {
     b->tab_tfcap[f] = tfc[f]; b->tab_flcap[f] = flc[f]; b->tab_off[f] = off;
     for (uint32_t tf = 0; tf < tfc[f]; ++tf)
-      for (uint32_t fl = 0; fl < flc[f]; ++fl) h.push_back(tf == 0 ? 0.0 : bm25_tf_host(b->k1, b->b, ix->avg[f], tf, fl));
+      for (uint32_t fl = 0; fl < flc[f]; ++fl) h.push_back((tf == 0 ? 0.0 : bm25_tf_host(b->k1, b->b, ix->avg[f], tf, fl)) * b->tab_scale[f]);
     off += tfc[f] * flc[f];
   }
   b->tab_total = off;
@@ -606,8 +624,7 @@ int batch_load(pb_batch* b, const pb_query_batch_desc* d, uint64_t full_cap, boo
   if (full_cap) {
     CU(b->full_q.ensure(full_cap)); CU(b->full_doc.ensure(full_cap)); CU(b->full_score.ensure(full_cap));
   }
-  if (b->scorer == PB_SCORER_BM25 &&
-      !(b->tab_valid && b->tab_k1 == b->k1 && b->tab_b == b->b && b->tab_epoch == ix->live_epoch)) {
+  if (b->scorer == PB_SCORER_BM25 && !batch_table_current(b)) {
     RC(batch_build_table(b));             // (k1, b, avg) unchanged since the last batch staged here: the table stays
     b->tab_valid = true; b->tab_k1 = b->k1; b->tab_b = b->b;
     b->tab_epoch = ix->live_epoch;
@@ -719,7 +736,7 @@ int batch_compute(pb_batch* b) {
   b->ran = false; b->gathered = false; b->gather_pending = false;
   b->rev_used = 0;
   for (auto& v : b->rev_span) v.clear();
-  if (b->scorer == PB_SCORER_BM25 && b->tab_epoch != ix->live_epoch) {     // pb_index_set_live_state since staging: new avg
+  if (b->scorer == PB_SCORER_BM25 && !batch_table_current(b)) {     // pb_index_set_live_state since staging: new avg
     RC(batch_build_table(b));
     b->tab_epoch = ix->live_epoch;
     b->tab_valid = true; b->tab_k1 = b->k1; b->tab_b = b->b;
@@ -901,7 +918,7 @@ int batch_compute(pb_batch* b) {
   P.out.results_total = b->full_count.p + 1;
   P.query_term_off = b->query_term_off.p;
   P.k1 = b->k1; P.b = b->b; P.one_minus_b = 1.0 - b->b; P.k1_plus_1 = b->k1 + 1.0;
-  for (int f = 0; f < 4; ++f) { P.boost[f] = b->boost[f]; P.avg[f] = ix->avg[f]; P.tab_tfcap[f] = b->tab_tfcap[f]; P.tab_flcap[f] = b->tab_flcap[f]; P.tab_off[f] = b->tab_off[f]; }
+  for (int f = 0; f < 4; ++f) { P.tab_scale[f] = b->scorer == PB_SCORER_BM25 ? b->tab_scale[f] : 1.0; P.boost[f] = P.tab_scale[f] != 1.0 ? 1.0 : b->boost[f]; P.avg[f] = ix->avg[f]; P.tab_tfcap[f] = b->tab_tfcap[f]; P.tab_flcap[f] = b->tab_flcap[f]; P.tab_off[f] = b->tab_off[f]; }
   P.tab = b->tab.p; P.tab_total = b->scorer == 0 ? b->tab_total : 0;
   P.tab_full = b->tab_full ? 1u : 0u;
   // tiles PB_L2_AHEAD ahead are pulled into L2 (measured on cfg 1, whose image is only 207 MB: 25.1 ms with the prefetch,
@@ -909,7 +926,7 @@ int batch_compute(pb_batch* b) {
   P.l2_prefetch = 1u;
   if (const char* e = std::getenv("PB_L2_PREFETCH")) P.l2_prefetch = atoi(e) ? 1u : 0u;
   P.boosts_all_one = 1u;
-  for (uint32_t f = 0; f < ix->F; ++f) if (b->boost[f] != 1.0) P.boosts_all_one = 0u;
+  for (uint32_t f = 0; f < ix->F; ++f) if (P.boost[f] != 1.0) P.boosts_all_one = 0u;      // folded boosts count as 1.0
   P.doc_bits = doc_bits; P.bitmap_words = bitmap_words; P.bitmap_sum_words = bitmap_sum_words; P.bitmap_doc_words = bitmap_doc_words;
   P.xcount = b->xcount.p; P.xtiles = b->xcount.p + 1;
   P.q_bmoff = b->q_bmoff.p; P.q_prim = b->q_prim.p;

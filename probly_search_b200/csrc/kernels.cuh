@@ -176,7 +176,11 @@ struct ScoreParams {
   const uint64_t* query_term_off;// query_terms_len = off[q+1]-off[q] (query.rs:32)
   // BM25
   double k1, b, one_minus_b, k1_plus_1;
-  double boost[4];
+  double boost[4];               // fields_boost, with 1.0 for the fields whose boost is folded into the table (tab_scale)
+  // A boost that is +-2^k multiplies exactly, and exact scaling commutes with every rounding of the score chain
+  // ((tf' * idf) * boost) * eb  ==  ((tf' * boost) * idf) * eb  bit for bit - so the host folds it into the table of
+  // saturated tf (and bm25_tf_slow applies it to values outside the table) and the loop skips that multiplication.
+  double tab_scale[4];
   double avg[4];
   const double* tab;             // [F][tfcap][flcap] saturated tf (bm25.rs:78-82), host-computed
   uint32_t tab_tfcap[4], tab_flcap[4], tab_off[4], tab_total;
@@ -283,7 +287,7 @@ __device__ __forceinline__ double bm25_tf_slow(const ScoreParams& P, uint32_t tf
   double ratio = __ddiv_rn((double)fl, P.avg[f]);
   double inner = __dadd_rn(P.one_minus_b, __dmul_rn(P.b, ratio));
   double den = __dadd_rn(__dmul_rn(P.k1, inner), tfd);
-  return __ddiv_rn(num, den);
+  return __dmul_rn(__ddiv_rn(num, den), P.tab_scale[f]);     // 1.0 unless a power-of-two boost is folded in (exact)
 }
 
 // zero_to_one.rs:72 — 1 - |explen - qlen| / explen  (byte lengths)

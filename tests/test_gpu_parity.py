@@ -186,6 +186,29 @@ def test_removed_docs_by_row_bits_and_by_bitmap_probe(monkeypatch, row_dead, cfg
         assert ix.last_stats()["pointer_visits"] == exp["score_calls"]
 
 
+@pytest.mark.parametrize("boosts", [[2.0, 0.5], [4.0, 0.25], [-2.0, 1.5], [0.5, 3.0], [1.0, 0.125]])
+def test_power_of_two_boosts_folded_into_the_table(monkeypatch, boosts):
+    """A boost of +-2^k is folded into the table of saturated tf (ScoreParams::tab_scale): exact, so the scores must be
+    the oracle's bit for bit, folded (default) or not (PB_FOLD_BOOST=0), for mixed folded / unfolded fields, and when
+    the same staged batch's boosts change between runs."""
+    cfg, ix, o, fq, scorer = _scaled("cfg1", 30_000, 1 << 11, 150)
+    exp = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, orc.BM25, boosts, 10)
+    for fold in ("1", "0", "1"):
+        monkeypatch.setenv("PB_FOLD_BOOST", fold)
+        got = ix.query_batch_flat(fq, score.bm25.new(), boosts, 10)
+        np.testing.assert_array_equal(got.n_results, exp["n_results"])
+        np.testing.assert_array_equal(got.doc_digest, exp["doc_digest"])
+        np.testing.assert_array_equal(got.score_digest, exp["score_digest"])
+        for q in range(fq.n_queries):
+            n = int(got.topk_n[q])
+            np.testing.assert_array_equal(got.topk_doc[q, :n], exp["topk_key"][q, :n].astype(np.uint32))
+            np.testing.assert_array_equal(got.topk_score[q, :n], exp["topk_score"][q, :n])
+        # unit boosts next through the same scratch batch: the folded table must not survive
+        one = ix.query_batch_flat(fq, score.bm25.new(), [1.0, 1.0], 10)
+        e1 = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, orc.BM25, [1.0, 1.0], 10)
+        np.testing.assert_array_equal(one.score_digest, e1["score_digest"])
+
+
 def test_full_results_sample_matches_oracle():
     cfg, ix, o, fq, scorer = _scaled("cfg1", 30_000, 1 << 12, 40)
     qi, docs, scores = ix.query_full_flat(fq, CALC[scorer](), cfg.boosts)
