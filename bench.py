@@ -570,6 +570,21 @@ def run_config(ctx, cfg):
         latency = {"queries": nl, "p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)),
                    "mean_us": float(ts.mean()), "launches_per_query": ix.last_stats()["gpu_launches"],
                    "what": "pb_query_batch with ONE query, host buffers in and out (top_k results), wall clock"}
+        # the same calls from 4 host threads at once: the library lends each an internal batch (own stream), so they overlap
+        import threading
+        ones = [fq.slice(q, q + 1) for q in range(nl)]
+        for nthr in (1, 4):
+            def worker(t):
+                for q in range(t, nl, nthr):
+                    ix.query_batch_flat(ones[q], calc, cfg.boosts, k)
+            for rep in range(2):                       # the first pass creates the borrowed batches and their workspaces
+                th = [threading.Thread(target=worker, args=(t,)) for t in range(nthr)]
+                t1 = time.perf_counter()
+                for x in th:
+                    x.start()
+                for x in th:
+                    x.join()
+                latency[f"qps_{nthr}_threads"] = nl / (time.perf_counter() - t1)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on the host cores, bounded sample
     cpu = None

@@ -17,7 +17,10 @@
  * calls, which need the same exclusion against running batches; each pb_batch owns its workspace
  * and stream, so DIFFERENT pb_batch objects on one index may run concurrently from different host
  * threads (mirrors `query(&self, ..)`, src/query.rs:22).  The one-call forms pb_query_batch /
- * pb_query_full / pb_index_expand_term share one internal batch per index and serialise on it.
+ * pb_query_full / pb_index_expand_term borrow one of a few internal batches per index (PB_QUERY_SLOTS, default 4:
+ * own stream and workspace each), so calls from different host threads overlap on the device; they exclude the
+ * calls that change the index (pb_index_set_live_state, pb_index_set_df_extra, pb_index_attach_delta), which wait
+ * for running one-call queries and hold new ones back.  pb_index_last_stats = the call that finished last.
  * A staged pb_batch follows pb_index_set_live_state: its BM25 table is rebuilt when the index's
  * live state changed since it was staged.
  *

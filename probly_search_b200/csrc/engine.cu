@@ -13,7 +13,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -153,8 +155,16 @@ struct pb_index {
   // delta segment (pb_index_attach_delta): the rows of the documents added behind this image, under the current trie
   pb_index* delta = nullptr;     // owned
   std::vector<uint32_t> sid;     // builder term id of every term ordinal of THIS image (matches terms across the segments)
-  std::mutex mu;                 // guards `scratch`
-  pb_batch* scratch = nullptr;   // reused by pb_query_batch / pb_query_full / expand_term
+  // pb_query_batch / pb_query_full / pb_index_expand_term borrow one of a few internal batches (own stream + workspace
+  // each), so calls from different host threads overlap on the device; they hold state_mu shared, the calls that
+  // change the index (pb_index_set_live_state, pb_index_set_df_extra, pb_index_attach_delta) hold it exclusively.
+  std::shared_mutex state_mu;
+  std::mutex pool_mu;            // guards the four members below
+  std::condition_variable pool_cv;
+  std::vector<pb_batch*> pool_free;
+  int pool_size = 0;
+  pb_batch_stats last_st{};      // stats of the most recently finished one-call query (pb_index_last_stats)
+  bool has_last = false;
 
   UnionView uview() const {
     UnionView u;
@@ -1246,11 +1256,38 @@ int batch_fetch_enqueue(pb_batch* b, pb_query_results* o) {
   return PB_OK;
 }
 
-int index_scratch(pb_index* ix, pb_batch** out) {
-  if (!ix->scratch) RC(batch_new(ix, &ix->scratch));
-  *out = ix->scratch;
-  return PB_OK;
-}
+// One internal batch, borrowed for the duration of a one-call query (see pb_index::state_mu).  At most PB_QUERY_SLOTS
+// (default 4) exist per index; a fifth concurrent caller waits for one to come back.
+struct ScratchLease {
+  pb_index* ix;
+  pb_batch* b = nullptr;
+  std::shared_lock<std::shared_mutex> rd;
+  explicit ScratchLease(pb_index* i) : ix(i), rd(i->state_mu) {}
+  ScratchLease(const ScratchLease&) = delete;
+  ScratchLease& operator=(const ScratchLease&) = delete;
+  int acquire() {
+    static const int max_slots = [] { const char* e = std::getenv("PB_QUERY_SLOTS"); return e ? std::min(16, std::max(1, atoi(e))) : 4; }();
+    std::unique_lock<std::mutex> lk(ix->pool_mu);
+    for (;;) {
+      if (!ix->pool_free.empty()) { b = ix->pool_free.back(); ix->pool_free.pop_back(); return PB_OK; }
+      if (ix->pool_size < max_slots) {
+        ++ix->pool_size;
+        lk.unlock();
+        int rc = batch_new(ix, &b);
+        if (rc != PB_OK) { lk.lock(); --ix->pool_size; b = nullptr; ix->pool_cv.notify_one(); }
+        return rc;
+      }
+      ix->pool_cv.wait(lk);
+    }
+  }
+  ~ScratchLease() {
+    if (!b) return;
+    std::lock_guard<std::mutex> lk(ix->pool_mu);
+    ix->last_st = b->st; ix->has_last = true;
+    ix->pool_free.push_back(b);
+    ix->pool_cv.notify_one();
+  }
+};
 
 }  // namespace
 
@@ -1470,7 +1507,7 @@ int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t
                             const double* field_avg) {
   if (!ix || !field_avg || (n_removed && !removed_ords)) { pb::set_error("pb_index_set_live_state: null argument"); return PB_ERR_INVALID; }
   PB_TRY({
-    std::lock_guard<std::mutex> lk(ix->mu);
+    std::unique_lock<std::shared_mutex> lk(ix->state_mu);
     // with a delta segment the ordinals are those of the whole index: the main image takes the ones it covers
     const uint64_t n_all = ix->delta ? ix->delta->n_docs : ix->n_docs;
     std::vector<uint32_t> bm((ix->n_docs + 31) / 32 + 1, 0), bmd;
@@ -1501,7 +1538,7 @@ int pb_index_set_df_extra(pb_index* ix, const uint64_t* df_extra, uint64_t n) {
   if (!ix || (n && !df_extra)) { pb::set_error("pb_index_set_df_extra: null argument"); return PB_ERR_INVALID; }
   if (n != 0 && n != ix->n_terms) { pb::set_error("pb_index_set_df_extra: %llu entries, the image has %llu terms", (ull)n, (ull)ix->n_terms); return PB_ERR_INVALID; }
   PB_TRY({
-    std::lock_guard<std::mutex> lk(ix->mu);
+    std::unique_lock<std::shared_mutex> lk(ix->state_mu);
     CU(cudaSetDevice(ix->device));
     ix->h_df_extra.assign(df_extra, df_extra + n);
     ++ix->live_epoch;
@@ -1513,7 +1550,7 @@ int pb_index_attach_delta(pb_index* ix, pb_index* delta, const uint32_t* main_te
                           const uint32_t* delta_term_ids, uint64_t n_delta_terms) {
   if (!ix) { pb::set_error("pb_index_attach_delta: null argument"); return PB_ERR_INVALID; }
   PB_TRY({
-    std::lock_guard<std::mutex> lk(ix->mu);
+    std::unique_lock<std::shared_mutex> lk(ix->state_mu);
     if (delta) {
       if (delta == ix || delta->delta) { pb::set_error("pb_index_attach_delta: a delta segment cannot have one of its own"); return PB_ERR_INVALID; }
       if (delta->device != ix->device || delta->F != ix->F) { pb::set_error("pb_index_attach_delta: the segments must live on one device and have the same fields"); return PB_ERR_INVALID; }
@@ -1538,7 +1575,7 @@ void pb_index_destroy(pb_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
   if (ix->delta) pb_index_destroy(ix->delta);
-  delete ix->scratch;
+  for (pb_batch* b : ix->pool_free) delete b;
   delete ix;
 }
 
@@ -1612,11 +1649,11 @@ int pb_index_expand_term(pb_index* ix, const uint8_t* term, uint64_t term_len, u
   if (!ix || !n_expansions || !needed || (term_len && !term)) { pb::set_error("pb_index_expand_term: null argument"); return PB_ERR_INVALID; }
   if (ix->delta) { pb::set_error("pb_index_expand_term: the index has a delta segment (fold it in first)"); return PB_ERR_UNSUPPORTED; }
   PB_TRY({
-    std::lock_guard<std::mutex> lk(ix->mu);
     *n_expansions = 0; *needed = 0;
     if (!pb::utf8_valid(term, term_len)) { pb::set_error("pb_index_expand_term: invalid UTF-8"); return PB_ERR_INVALID; }
-    pb_batch* b = nullptr;
-    RC(index_scratch(ix, &b));
+    ScratchLease lease(ix);
+    RC(lease.acquire());
+    pb_batch* b = lease.b;
     CU(cudaSetDevice(ix->device));
     uint64_t off[2] = {0, term_len};
     CU(b->term_bytes.ensure(term_len + 16)); CU(b->term_byte_off.ensure(3));
@@ -1779,9 +1816,9 @@ int pb_batch_get_stats(const pb_batch* b, pb_batch_stats* out) {
 
 static int query_batch_one(pb_index* ix, const pb_query_batch_desc* q, pb_query_results* out) {
   PB_TRY({
-    std::lock_guard<std::mutex> lk(ix->mu);
-    pb_batch* b = nullptr;
-    RC(index_scratch(ix, &b));
+    ScratchLease lease(ix);
+    RC(lease.acquire());
+    pb_batch* b = lease.b;
     // one call = upload + kernels + download with as few host round trips as the planning allows: the caller's
     // buffers stay valid for the whole call, so nothing waits for the uploads, and the result copies are
     // enqueued BEFORE the run's final synchronisation (small batches: one copy of the packed block into a pinned
@@ -1858,17 +1895,19 @@ int pb_query_batch(pb_index* ix, const pb_query_batch_desc* q, pb_query_results*
 }
 
 int pb_index_last_stats(pb_index* ix, pb_batch_stats* out) {
-  if (!ix || !out || !ix->scratch) return PB_ERR_INVALID;
-  *out = ix->scratch->st;
+  if (!ix || !out) return PB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ix->pool_mu);
+  if (!ix->has_last) return PB_ERR_INVALID;
+  *out = ix->last_st;
   return PB_OK;
 }
 
 static int query_full_one(pb_index* ix, const pb_query_batch_desc* q, uint64_t cap, uint32_t* out_query, uint32_t* out_doc,
                           double* out_score, uint64_t* n_total) {
   PB_TRY({
-    std::lock_guard<std::mutex> lk(ix->mu);
-    pb_batch* b = nullptr;
-    RC(index_scratch(ix, &b));
+    ScratchLease lease(ix);
+    RC(lease.acquire());
+    pb_batch* b = lease.b;
     pb_query_batch_desc d = *q;
     RC(batch_load(b, &d, std::max<uint64_t>(cap, 1)));
     int rc = batch_run(b);

@@ -350,3 +350,38 @@ def test_index_served_from_an_image_file(tmp_path):
     np.testing.assert_array_equal(a.topk_score, b.topk_score)
     assert ld.expand_term("a") == ix.expand_term("a")
     ld.close()
+
+
+def test_one_call_queries_from_several_host_threads():
+    """pb_query_batch from 4 host threads at once on ONE index (each call borrows an internal batch, own stream):
+    every answer must be the oracle's, whatever the interleaving; a removal in between excludes running queries."""
+    import threading
+    cfg, ix, o, fq, scorer = _scaled("cfg1", 40_000, 1 << 11, 96)
+    k = 5
+    exp = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, scorer, cfg.boosts, k)
+    ix.query_batch_flat(fq.slice(0, 1), CALC[scorer](), cfg.boosts, k)         # image resident before the threads start
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(3):
+                for q in range(t, fq.n_queries, 4):
+                    n = 1 if (q + rep) % 3 else min(7, fq.n_queries - q)     # single queries and small batches mixed
+                    r = ix.query_batch_flat(fq.slice(q, q + n), CALC[scorer](), cfg.boosts, k)
+                    for j in range(n):
+                        assert int(r.n_results[j]) == int(exp["n_results"][q + j])
+                        assert int(r.doc_digest[j]) == int(exp["doc_digest"][q + j])
+                        assert int(r.score_digest[j]) == int(exp["score_digest"][q + j])
+                        m = int(r.topk_n[j])
+                        assert m == int(exp["topk_n"][q + j])
+                        assert r.topk_doc[j, :m].tolist() == exp["topk_key"][q + j, :m].astype(np.uint32).tolist()
+        except Exception as e:          # surfaced in the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert ix.last_stats()["n_queries"] >= 1
