@@ -309,7 +309,7 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
   ++ix->live_epoch;
   // the same bitmap per posting row, for the scoring loop (PB_ROW_DEAD=0: keep probing the doc bitmap - A/B and tests)
   ix->row_dead_ok = false;
-  if (n_removed && ix->n_rows) {
+  if (n_removed && ix->n_rows && ix->narrow) {          // the wide layout's loop probes the bitmap (process_tile)
     const char* e = std::getenv("PB_ROW_DEAD");
     if (!(e && !std::strcmp(e, "0"))) {
       const uint64_t tiles = ix->n_rows_padded / TILE_ROWS;
