@@ -270,7 +270,8 @@ class Index:
         ords = np.ascontiguousarray(np.nonzero(bits)[0], dtype=np.uint32)
         avg = (C.c_double * 4)(*[im.field_avg[i] for i in range(4)])
         capi.check(self._L.pb_index_set_live_state(self._ix, ords.ctypes.data, len(ords), im.n_live_docs, avg))
-        self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
+        if self._ord_to_id is None or len(self._ord_to_id) != nd:      # ordinals -> keys only change when docs are added / vacuumed
+            self._ord_to_id = np.ctypeslib.as_array(im.doc_key, shape=(nd,)).copy() if nd else np.zeros(0, np.uint64)
 
     def _drop_delta(self) -> None:
         if self._ix_delta is not None:
