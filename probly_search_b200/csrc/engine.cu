@@ -13,7 +13,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <atomic>
 #include <condition_variable>
+#include <thread>
 #include <mutex>
 #include <shared_mutex>
 #include <string>
@@ -159,6 +161,7 @@ struct pb_index {
   // each), so calls from different host threads overlap on the device; they hold state_mu shared, the calls that
   // change the index (pb_index_set_live_state, pb_index_set_df_extra, pb_index_attach_delta) hold it exclusively.
   std::shared_mutex state_mu;
+  std::atomic<int> writers_waiting{0};   // one-call queries stand back while a state change waits (no writer starvation)
   std::mutex pool_mu;            // guards the four members below
   std::condition_variable pool_cv;
   std::vector<pb_batch*> pool_free;
@@ -295,6 +298,7 @@ static int index_upload_idf(pb_index* ix) {
   }
   CU(ix->term_idf.ensure(NT + 1));
   CU(cudaMemcpy(ix->term_idf.p, idf.data(), (NT + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaDeviceSynchronize());     // see index_apply_live_state: the DMA of a pageable copy may still be in flight
   return PB_OK;
 }
 
@@ -355,6 +359,8 @@ static int index_apply_live_state(pb_index* ix, const uint32_t* bitmap_words, ui
   RC(index_upload_idf(ix));
   CU(cudaMemcpy(ix->live_prefix.p, lp.data(), (NT + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ix->liverows_prefix.p, lrp.data(), (NT + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  // a cudaMemcpy from pageable memory may return before its DMA has landed; the batches run on non-blocking streams
+  CU(cudaDeviceSynchronize());
   return PB_OK;
 }
 
@@ -1256,13 +1262,27 @@ int batch_fetch_enqueue(pb_batch* b, pb_query_results* o) {
   return PB_OK;
 }
 
+// Exclusive side of pb_index::state_mu: announces itself first, so that new one-call queries wait behind it.
+struct StateChange {
+  pb_index* ix;
+  std::unique_lock<std::shared_mutex> wr;
+  explicit StateChange(pb_index* i) : ix(i), wr(i->state_mu, std::defer_lock) {
+    ix->writers_waiting.fetch_add(1, std::memory_order_acq_rel);
+    wr.lock();
+    ix->writers_waiting.fetch_sub(1, std::memory_order_acq_rel);
+  }
+};
+
 // One internal batch, borrowed for the duration of a one-call query (see pb_index::state_mu).  At most PB_QUERY_SLOTS
 // (default 4) exist per index; a fifth concurrent caller waits for one to come back.
 struct ScratchLease {
   pb_index* ix;
   pb_batch* b = nullptr;
   std::shared_lock<std::shared_mutex> rd;
-  explicit ScratchLease(pb_index* i) : ix(i), rd(i->state_mu) {}
+  explicit ScratchLease(pb_index* i) : ix(i), rd(i->state_mu, std::defer_lock) {
+    while (ix->writers_waiting.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    rd.lock();
+  }
   ScratchLease(const ScratchLease&) = delete;
   ScratchLease& operator=(const ScratchLease&) = delete;
   int acquire() {
@@ -1507,7 +1527,7 @@ int pb_index_set_live_state(pb_index* ix, const uint32_t* removed_ords, uint64_t
                             const double* field_avg) {
   if (!ix || !field_avg || (n_removed && !removed_ords)) { pb::set_error("pb_index_set_live_state: null argument"); return PB_ERR_INVALID; }
   PB_TRY({
-    std::unique_lock<std::shared_mutex> lk(ix->state_mu);
+    StateChange lk(ix);
     // with a delta segment the ordinals are those of the whole index: the main image takes the ones it covers
     const uint64_t n_all = ix->delta ? ix->delta->n_docs : ix->n_docs;
     std::vector<uint32_t> bm((ix->n_docs + 31) / 32 + 1, 0), bmd;
@@ -1538,7 +1558,7 @@ int pb_index_set_df_extra(pb_index* ix, const uint64_t* df_extra, uint64_t n) {
   if (!ix || (n && !df_extra)) { pb::set_error("pb_index_set_df_extra: null argument"); return PB_ERR_INVALID; }
   if (n != 0 && n != ix->n_terms) { pb::set_error("pb_index_set_df_extra: %llu entries, the image has %llu terms", (ull)n, (ull)ix->n_terms); return PB_ERR_INVALID; }
   PB_TRY({
-    std::unique_lock<std::shared_mutex> lk(ix->state_mu);
+    StateChange lk(ix);
     CU(cudaSetDevice(ix->device));
     ix->h_df_extra.assign(df_extra, df_extra + n);
     ++ix->live_epoch;
@@ -1550,7 +1570,7 @@ int pb_index_attach_delta(pb_index* ix, pb_index* delta, const uint32_t* main_te
                           const uint32_t* delta_term_ids, uint64_t n_delta_terms) {
   if (!ix) { pb::set_error("pb_index_attach_delta: null argument"); return PB_ERR_INVALID; }
   PB_TRY({
-    std::unique_lock<std::shared_mutex> lk(ix->state_mu);
+    StateChange lk(ix);
     if (delta) {
       if (delta == ix || delta->delta) { pb::set_error("pb_index_attach_delta: a delta segment cannot have one of its own"); return PB_ERR_INVALID; }
       if (delta->device != ix->device || delta->F != ix->F) { pb::set_error("pb_index_attach_delta: the segments must live on one device and have the same fields"); return PB_ERR_INVALID; }

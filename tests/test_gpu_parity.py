@@ -385,3 +385,54 @@ def test_one_call_queries_from_several_host_threads():
         t.join()
     assert not errors, errors[:3]
     assert ix.last_stats()["n_queries"] >= 1
+
+
+def test_live_state_change_while_other_threads_query():
+    """pb_index_set_live_state takes the index exclusively: a one-call query running in another host thread sees the
+    state before or after it, never a mixture (idf / avg / removed mask / BM25 table of different states)."""
+    import threading
+    cfg = W.CONFIGS["cfg1"]
+    n_docs, vocab = 40_000, 1 << 11
+    wl = W.Workload(cfg, n_docs=n_docs, vocab=vocab)
+    ix, ix2, o = Index(cfg.n_fields), Index(cfg.n_fields), orc.OracleIndex(cfg.n_fields)
+    for x in (ix, ix2, o):
+        wl.build_into(x)
+    fq = wl.queries(64)
+    k = 5
+    before = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, orc.BM25, cfg.boosts, k)
+    gone = W.Workload(W.CONFIGS["cfg4"], n_docs=n_docs, vocab=vocab).removed_ordinals()
+    for d in gone:
+        ix2.remove_document(int(d))
+        o.remove_document(int(d))
+    after = o.query_batch_flat(fq.query_term_off, fq.term_bytes, fq.term_byte_off, orc.BM25, cfg.boosts, k)
+    ords, n_live, avg = ix2.live_state()
+    ix.query_batch_flat(fq.slice(0, 1), score.bm25.new(), cfg.boosts, k)
+    errors, seen = [], {"before": 0, "after": 0}
+    stop = threading.Event()
+
+    def worker(t):
+        try:
+            q = t
+            while not stop.is_set():
+                r = ix.query_batch_flat(fq.slice(q, q + 1), score.bm25.new(), cfg.boosts, k)
+                got = (int(r.n_results[0]), int(r.doc_digest[0]), int(r.score_digest[0]))
+                b = (int(before["n_results"][q]), int(before["doc_digest"][q]), int(before["score_digest"][q]))
+                a = (int(after["n_results"][q]), int(after["doc_digest"][q]), int(after["score_digest"][q]))
+                assert got == b or got == a, (q, got, b, a)
+                seen["before" if got == b else "after"] += 1
+                q = (q + 3) % fq.n_queries
+        except Exception as e:
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(3)]
+    for t in threads:
+        t.start()
+    import time as _t
+    _t.sleep(0.05)
+    ix.set_live_state(ords, n_live, avg)          # C-level call only: the host mirror of `ix` is not touched
+    _t.sleep(0.05)
+    stop.set()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert seen["after"] > 0
