@@ -100,13 +100,13 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(cfg_name: str, kernel_class: str):
-    """dram bytes per launch of the dominant kernel from a committed ncu capture of THIS config and
-    launch class (profiles/roofline_traffic.json); anything else is not this kernel's traffic -> None."""
+def ncu_traffic(cfg_name: str, kernel_class: str, queries_per_gpu: int):
+    """dram bytes per launch of the dominant kernel from a committed ncu capture of THIS config, launch class and
+    batch size per GPU (profiles/roofline_traffic.json); anything else is not this launch's traffic -> None."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         e = d.get(cfg_name)
-        if e and e.get("class") == kernel_class:
+        if e and e.get("class") == kernel_class and e.get("queries_per_gpu", queries_per_gpu) == queries_per_gpu:
             return e
     except Exception:
         pass
@@ -529,7 +529,7 @@ def run_config(ctx, cfg):
             gb = C.c_double(0.0)
             if L.pb_device_read_bandwidth(local_rank, nbytes, iters, C.byref(gb)) == 0:
                 ceilings[name] = gb.value
-    tr = ncu_traffic(cfg.name, dom_name)
+    tr = ncu_traffic(cfg.name, dom_name, nq_local)
     image_fits_l2 = lay["posting_bytes"] < 2 * L2_BYTES
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "class": dom_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
